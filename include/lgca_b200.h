@@ -1,0 +1,174 @@
+/*
+ * lgca_b200.h -- C-ABI of the B200-native LGCA engine (liblgca_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of keva92/lgca: everything the reference's
+ * `Lattice<Model>` backend interface (src/lattice.h:32-238; the five pure virtuals at :187-203 and the
+ * three copy hooks at :206-211, implemented on the CPU by OMP_Lattice, src/omp_lattice.cpp) needs from
+ * a device backend, as plain C: opaque handle, plain pointers and sizes, int status codes.  The C++
+ * `B200_Lattice<Model>` (lgca_b200/host/b200_lattice.h) is the binding a reference maintainer would
+ * add next to OMP_Lattice; INTEGRATION.md shows it.
+ *
+ * Host-side array layouts are the reference's own (so existing apps keep working unchanged):
+ *   state      uint8[dim_x*dim_y]      bit d of byte `cell` = occupation of direction d
+ *                                      (src/omp_lattice.cpp:179,237; src/lgca_bitset.h:229-231)
+ *   cell_type  int32[dim_x*dim_y]      0 FLUID, 1 SOLID_NO_SLIP, 2 SOLID_SLIP (src/lgca_common.h:53-57)
+ *   rnd_bits   uint8[ceil(cells/8)]    chirality bit of cell i = bit i%8 of byte i/8
+ *                                      (src/lgca_bitset.h:220-231; read at src/omp_lattice.cpp:198)
+ *   cell = y*dim_x + x; y = 0 is the southern row.
+ * On the device the lattice lives as bit-planes (one 32-bit word = 32 sites of one direction); that
+ * layout is private to the library.
+ *
+ * Every function returns 0 on success and a negative LGCA_B200_E* code on failure;
+ * lgca_b200_last_error() returns a message for the calling thread.  There is NO CPU fallback: without
+ * a CUDA device every compute entry point fails with LGCA_B200_ENODEV.
+ *
+ * Threading (reference: apps/pipe/pipe_viewer.cpp:105,150 runs stepping and post-processing on two
+ * host threads): {step, body force, snapshot, upload, download} use the handle's compute stream,
+ * {post_process, mean_velocity, count on snapshot} use its post-processing stream; the snapshot buffer
+ * separates them and event ordering makes the pair safe to call concurrently from two threads.
+ */
+#ifndef LGCA_B200_H_
+#define LGCA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LGCA_B200_VERSION 1
+
+/* models: enum class Model, src/lgca_common.h:46-51 */
+enum { LGCA_B200_HPP = 0, LGCA_B200_FHP_I = 1, LGCA_B200_FHP_II = 2, LGCA_B200_FHP_III = 3 };
+
+/* status codes */
+enum {
+    LGCA_B200_OK      = 0,
+    LGCA_B200_EINVAL  = -1, /* bad argument */
+    LGCA_B200_ENODEV  = -2, /* no CUDA device / wrong architecture: the product has no CPU path */
+    LGCA_B200_ECUDA   = -3, /* CUDA runtime error (message in last_error) */
+    LGCA_B200_ENOMEM  = -4,
+    LGCA_B200_ESTATE  = -5  /* call order violated (e.g. step before upload) */
+};
+
+/* lgca_b200_config.flags */
+enum {
+    LGCA_B200_FLAG_NO_CELL_FIELDS = 1u << 0, /* never produce per-cell float fields (>= 1e9-cell runs) */
+    LGCA_B200_FLAG_SIMPLE_KERNEL  = 1u << 1  /* force the one-word-per-thread kernel (debug / A-B tests) */
+};
+
+typedef struct lgca_b200_lattice lgca_b200_lattice; /* opaque */
+
+typedef struct {
+    int32_t  model;    /* LGCA_B200_HPP .. LGCA_B200_FHP_III */
+    uint32_t dim_x;    /* global lattice width  (Lattice::m_dim_x, src/lattice.h:43) */
+    uint32_t dim_y;    /* global lattice height (Lattice::m_dim_y; even for FHP, src/lattice.cpp:141) */
+    uint32_t cg_radius;/* coarse graining radius (src/lattice.h:51); 0 = no coarse fields */
+    int32_t  bf_dir;   /* body force direction 'x', 'y' or 0 (Lattice::m_bf_dir, src/lattice.cpp:125-133) */
+    int32_t  device;   /* CUDA device ordinal */
+    int32_t  k_fuse;   /* time steps fused per HBM pass (temporal blocking); 0 = library default */
+    uint32_t y_begin;  /* first global row of the strip this handle owns (multi-GPU row strips) */
+    uint32_t y_rows;   /* rows in the strip; 0 = the whole lattice (single GPU) */
+    uint32_t flags;
+} lgca_b200_config;
+
+/* ---- life cycle: OMP_Lattice ctor/dtor + allocate_memory, src/omp_lattice.cpp:74-98,457-489 ---- */
+int  lgca_b200_create(const lgca_b200_config* cfg, lgca_b200_lattice** out);
+int  lgca_b200_destroy(lgca_b200_lattice* h);
+const char* lgca_b200_last_error(void);
+int  lgca_b200_version(void);
+/* number of usable CUDA devices (0 when there is none; never fails) */
+int  lgca_b200_device_count(void);
+
+/* pinned host memory for the reference-layout mirrors (OMP_Lattice::allocate_memory uses malloc,
+ * src/omp_lattice.cpp:457-471; pinned pages let uploads/downloads run at full PCIe speed) */
+int  lgca_b200_host_alloc(size_t bytes, void** out);
+int  lgca_b200_host_free(void* p);
+
+/* ---- Lattice::copy_data_to_device(), src/lattice.h:206 / src/lattice.cpp:422-427 (empty hook) ----
+ * Packs the reference-layout host arrays of the handle's strip into device bit-planes.  Any pointer
+ * may be NULL to keep what is already on the device (state NULL => keep particles, etc.).  Host
+ * arrays cover the STRIP's rows only: state/cell_type index = (y - y_begin)*dim_x + x; rnd_bits is
+ * always indexed by the GLOBAL cell number (it is one flat bit-field in the reference). */
+int  lgca_b200_upload(lgca_b200_lattice* h, const uint8_t* state, const int32_t* cell_type,
+                      const uint8_t* rnd_bits);
+/* ---- Lattice::copy_data_from_device(), src/lattice.h:209 ---- unpack + download the strip's state */
+int  lgca_b200_download(lgca_b200_lattice* h, uint8_t* state);
+
+/* ---- Lattice::collide_and_propagate(), src/lattice.h:191 / src/omp_lattice.cpp:100-249 ----
+ * n_steps successive updates (periodic pull-stream, then collide / bounce at the destination cell).
+ * Asynchronous on the compute stream.  The reference's `p` argument is ignored there and absent here
+ * (the chirality comes from the frozen rnd bit-field). */
+int  lgca_b200_step(lgca_b200_lattice* h, int n_steps);
+
+/* ---- Lattice::copy_data_to_output_buffer(), src/lattice.h:211 / src/lattice.cpp:437-441 ---- */
+int  lgca_b200_snapshot(lgca_b200_lattice* h);
+
+/* ---- Lattice::post_process(), src/lattice.h:203 / src/omp_lattice.cpp:349-454 ----
+ * Computes from the SNAPSHOT: per-cell density / momentum (AoS x,y) and the coarse-grained means over
+ * the reference's window.  NULL outputs are skipped.  `exact_order` != 0 reproduces the
+ * reference's float32 summation order for mean momentum y (bit-exact); 0 uses the popcount reduction
+ * (density and momentum x are bit-exact either way). Synchronous (results are in host memory on return). */
+int  lgca_b200_post_process(lgca_b200_lattice* h, float* cell_density, float* cell_momentum,
+                            float* mean_density, float* mean_momentum, int exact_order);
+
+/* ---- Lattice::get_mean_velocity(), src/lattice.h:194 / src/omp_lattice.cpp:508-557 ----
+ * Device reduction over the snapshot (double accumulation; NOT the reference's sequential float32
+ * order -- the order-exact variant runs in B200_Lattice on the host fields, as the reference does). */
+int  lgca_b200_mean_velocity(lgca_b200_lattice* h, float out[2]);
+
+/* ---- Lattice::apply_body_force(), src/lattice.h:200 / src/omp_lattice.cpp:254-346 ----
+ * Exact, draw-order-preserving body force.  `draws` are the caller's `rand()` values in stream order
+ * (each is reduced `% num_cells` like src/omp_lattice.cpp:269).  Draws are consumed in order until
+ * `forcing` particles have been reverted or `n_draws` are used up; *consumed and *reverted report the
+ * progress so the caller can continue with more draws (the reference stops after 2*num_cells draws;
+ * that cap is the caller's, see B200_Lattice::apply_body_force).  Operates on the live state. */
+int  lgca_b200_body_force(lgca_b200_lattice* h, int forcing, const int32_t* draws, size_t n_draws,
+                          size_t* consumed, uint32_t* reverted);
+
+/* ---- Lattice::get_n_particles(), src/lattice.h:165 / src/lattice.cpp:180-195 ---- (live state) */
+int  lgca_b200_count_particles(lgca_b200_lattice* h, uint64_t* out);
+
+/* ---- synthetic initial data for >= 1e8-cell throughput runs: occupancy with P = 1/NUM_DIR
+ * in FLUID cells and chirality with P = 1/2 from a counter-based hash of (seed, cell, dir), generated
+ * on the device.  Cell types must have been uploaded (or all-fluid via lgca_b200_fill_cell_type). ---- */
+int  lgca_b200_init_random_device(lgca_b200_lattice* h, uint64_t seed);
+/* paint a BC on the device for lattices too large to paint on the host:
+ * bc = "periodic" | "pipe" | "karman" | "reflecting_back" | "reflecting_forward" (src/lattice.cpp:221-334) */
+int  lgca_b200_apply_bc_device(lgca_b200_lattice* h, const char* bc);
+
+/* ---- streams / timing ---- */
+int  lgca_b200_sync(lgca_b200_lattice* h);
+/* cudaStream_t of the compute stream, for callers that time with their own CUDA events */
+void* lgca_b200_compute_stream(lgca_b200_lattice* h);
+/* Runs n_steps updates bracketed by CUDA events on the compute stream; returns the elapsed device time. */
+int  lgca_b200_timed_steps(lgca_b200_lattice* h, int n_steps, float* elapsed_ms);
+/* Kernel launches issued by this handle so far (bench.py's gpu_launches claim). */
+int  lgca_b200_launch_count(lgca_b200_lattice* h, uint64_t* out);
+
+/* ---- introspection ---- */
+typedef struct {
+    uint32_t dim_x, dim_y, y_begin, y_rows;
+    uint32_t words_per_row;     /* 32-bit words per bit-plane row */
+    uint32_t num_planes;        /* NUM_DIR */
+    uint32_t has_no_slip, has_slip;
+    int32_t  k_fuse;
+    uint64_t bytes_per_site_step_x8; /* algorithmic bits per site per step: 2*NUM_DIR + mask planes */
+    uint64_t device_bytes;      /* device memory held by the handle */
+} lgca_b200_info;
+int  lgca_b200_get_info(lgca_b200_lattice* h, lgca_b200_info* out);
+
+/* ---- multi-GPU row strips (one handle per GPU / process) ----
+ * Each strip keeps `halo` ghost rows above and below its own rows.  After every block of k fused steps
+ * the owner exports its k top and k bottom rows and imports its neighbours' (periodic ring in y, like
+ * the reference's always-periodic torus, src/omp_lattice.cpp:150-176).  The buffers are DEVICE
+ * pointers (packed bit-plane rows) so the caller moves them with NCCL send/recv or CUDA P2P copies. */
+int  lgca_b200_halo_bytes(lgca_b200_lattice* h, size_t* bytes_per_side);
+int  lgca_b200_halo_export(lgca_b200_lattice* h, void* dev_top_rows, void* dev_bottom_rows);
+int  lgca_b200_halo_import(lgca_b200_lattice* h, const void* dev_from_upper, const void* dev_from_lower);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LGCA_B200_H_ */

@@ -1,0 +1,243 @@
+"""ctypes binding of include/lgca_b200.h.  Fails loudly when the CUDA library is missing: there is no
+CPU path in this package."""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MODELS = {"HPP": 0, "FHP_I": 1, "FHP_II": 2, "FHP_III": 3}
+NUM_DIR = {0: 4, 1: 6, 2: 7, 3: 7}
+
+FLAG_NO_CELL_FIELDS = 1 << 0
+FLAG_SIMPLE_KERNEL = 1 << 1
+
+# every symbol include/lgca_b200.h declares (checked by tests/test_capi_symbols.py)
+SYMBOLS = [
+    "lgca_b200_create", "lgca_b200_destroy", "lgca_b200_last_error", "lgca_b200_version",
+    "lgca_b200_device_count", "lgca_b200_host_alloc", "lgca_b200_host_free", "lgca_b200_upload",
+    "lgca_b200_download", "lgca_b200_step", "lgca_b200_snapshot", "lgca_b200_post_process",
+    "lgca_b200_mean_velocity", "lgca_b200_body_force", "lgca_b200_count_particles",
+    "lgca_b200_init_random_device", "lgca_b200_apply_bc_device", "lgca_b200_sync",
+    "lgca_b200_compute_stream", "lgca_b200_timed_steps", "lgca_b200_launch_count", "lgca_b200_get_info",
+    "lgca_b200_halo_bytes", "lgca_b200_halo_export", "lgca_b200_halo_import",
+]
+
+
+class LgcaError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("model", C.c_int32), ("dim_x", C.c_uint32), ("dim_y", C.c_uint32), ("cg_radius", C.c_uint32),
+                ("bf_dir", C.c_int32), ("device", C.c_int32), ("k_fuse", C.c_int32), ("y_begin", C.c_uint32),
+                ("y_rows", C.c_uint32), ("flags", C.c_uint32)]
+
+
+class Info(C.Structure):
+    _fields_ = [("dim_x", C.c_uint32), ("dim_y", C.c_uint32), ("y_begin", C.c_uint32), ("y_rows", C.c_uint32),
+                ("words_per_row", C.c_uint32), ("num_planes", C.c_uint32), ("has_no_slip", C.c_uint32),
+                ("has_slip", C.c_uint32), ("k_fuse", C.c_int32), ("bytes_per_site_step_x8", C.c_uint64),
+                ("device_bytes", C.c_uint64)]
+
+
+def library_path():
+    return os.path.join(HERE, "liblgca_b200.so")
+
+
+_LIB = None
+
+
+def load_library():
+    """Load liblgca_b200.so; raise (never fall back) when it has not been built."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if not os.path.exists(path):
+        raise LgcaError("liblgca_b200.so is missing (%s): build it with `python -m lgca_b200.build` "
+                        "(__graft_entry__.build()); lgca_b200 has no CPU fallback" % path)
+    L = C.CDLL(path)
+    vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+    L.lgca_b200_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.lgca_b200_destroy.argtypes = [vp]
+    L.lgca_b200_last_error.restype = C.c_char_p
+    L.lgca_b200_host_alloc.argtypes = [C.c_size_t, C.POINTER(vp)]
+    L.lgca_b200_host_free.argtypes = [vp]
+    L.lgca_b200_upload.argtypes = [vp, vp, vp, vp]
+    L.lgca_b200_download.argtypes = [vp, vp]
+    L.lgca_b200_step.argtypes = [vp, i32]
+    L.lgca_b200_snapshot.argtypes = [vp]
+    L.lgca_b200_post_process.argtypes = [vp, vp, vp, vp, vp, i32]
+    L.lgca_b200_mean_velocity.argtypes = [vp, vp]
+    L.lgca_b200_body_force.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
+    L.lgca_b200_count_particles.argtypes = [vp, C.POINTER(u64)]
+    L.lgca_b200_init_random_device.argtypes = [vp, u64]
+    L.lgca_b200_apply_bc_device.argtypes = [vp, C.c_char_p]
+    L.lgca_b200_sync.argtypes = [vp]
+    L.lgca_b200_compute_stream.argtypes = [vp]
+    L.lgca_b200_compute_stream.restype = vp
+    L.lgca_b200_timed_steps.argtypes = [vp, i32, C.POINTER(C.c_float)]
+    L.lgca_b200_launch_count.argtypes = [vp, C.POINTER(u64)]
+    L.lgca_b200_get_info.argtypes = [vp, C.POINTER(Info)]
+    L.lgca_b200_halo_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
+    L.lgca_b200_halo_export.argtypes = [vp, vp, vp]
+    L.lgca_b200_halo_import.argtypes = [vp, vp, vp]
+    _LIB = L
+    return L
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class PinnedArray:
+    """numpy view over cudaHostAlloc'ed memory (host mirrors of the reference-layout arrays)."""
+
+    def __init__(self, shape, dtype):
+        L = load_library()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = C.c_void_p()
+        rc = L.lgca_b200_host_alloc(self.nbytes, C.byref(p))
+        if rc != 0:
+            raise LgcaError(L.lgca_b200_last_error().decode())
+        self._p = p
+        buf = (C.c_uint8 * max(self.nbytes, 1)).from_address(p.value)
+        self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+    def free(self):
+        if self._p:
+            self.array = None
+            load_library().lgca_b200_host_free(self._p)
+            self._p = None
+
+
+class Engine:
+    """One lattice (or one row strip of it) on one GPU -- a 1:1 wrapper of the C-ABI handle."""
+
+    def __init__(self, model, dim_x, dim_y, cg_radius=0, bf_dir=0, device=0, k_fuse=0, y_begin=0, y_rows=0, flags=0):
+        self.L = load_library()
+        self.model = MODELS[model] if isinstance(model, str) else int(model)
+        if isinstance(bf_dir, (bytes, str)):
+            bf_dir = ord(bf_dir) if bf_dir not in (b"\0", "\0", "", b"") else 0
+        cfg = Config(self.model, dim_x, dim_y, cg_radius, bf_dir, device, k_fuse, y_begin, y_rows, flags)
+        h = C.c_void_p()
+        self._check(self.L.lgca_b200_create(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.dim_x, self.dim_y = dim_x, dim_y
+        self.cg = cg_radius
+        self.num_dir = NUM_DIR[self.model]
+        i = self.info()
+        self.y_begin, self.y_rows = i.y_begin, i.y_rows
+        self.cells = self.dim_x * self.y_rows
+
+    def _check(self, rc):
+        if rc != 0:
+            raise LgcaError("lgca_b200 error %d: %s" % (rc, self.L.lgca_b200_last_error().decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.lgca_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # --- data movement (reference layouts) -----------------------------------------------------
+    def upload(self, state=None, cell_type=None, rnd_bits=None):
+        if state is not None:
+            state = np.ascontiguousarray(state, np.uint8)
+            assert state.size == self.cells
+        if cell_type is not None:
+            cell_type = np.ascontiguousarray(cell_type, np.int32)
+            assert cell_type.size == self.cells
+        if rnd_bits is not None:
+            rnd_bits = np.ascontiguousarray(rnd_bits, np.uint8)
+            assert rnd_bits.size >= (self.dim_x * self.dim_y + 7) // 8
+        self._check(self.L.lgca_b200_upload(self.h, _ptr(state), _ptr(cell_type), _ptr(rnd_bits)))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.cells, np.uint8)
+        self._check(self.L.lgca_b200_download(self.h, _ptr(out)))
+        return out
+
+    # --- the hot path ------------------------------------------------------------------------------
+    def step(self, n=1):
+        self._check(self.L.lgca_b200_step(self.h, int(n)))
+
+    def timed_steps(self, n):
+        ms = C.c_float(0)
+        self._check(self.L.lgca_b200_timed_steps(self.h, int(n), C.byref(ms)))
+        return float(ms.value)
+
+    def sync(self):
+        self._check(self.L.lgca_b200_sync(self.h))
+
+    def snapshot(self):
+        self._check(self.L.lgca_b200_snapshot(self.h))
+
+    def post_process(self, cell=True, mean=True, exact=True, out=None):
+        out = out or {}
+        n = self.cells
+        if cell:
+            out.setdefault("cell_density", np.empty(n, np.float32))
+            out.setdefault("cell_momentum", np.empty(2 * n, np.float32))
+        if mean:
+            nc = (self.dim_x // (2 * self.cg)) * (self.y_rows // (2 * self.cg))
+            out.setdefault("mean_density", np.empty(nc, np.float32))
+            out.setdefault("mean_momentum", np.empty(2 * nc, np.float32))
+        self._check(self.L.lgca_b200_post_process(self.h, _ptr(out.get("cell_density")), _ptr(out.get("cell_momentum")),
+                                                  _ptr(out.get("mean_density")), _ptr(out.get("mean_momentum")),
+                                                  1 if exact else 0))
+        return out
+
+    def mean_velocity(self):
+        out = np.zeros(2, np.float32)
+        self._check(self.L.lgca_b200_mean_velocity(self.h, _ptr(out)))
+        return out
+
+    def body_force(self, forcing, draws):
+        draws = np.ascontiguousarray(draws, np.int32)
+        used, rev = C.c_size_t(0), C.c_uint32(0)
+        self._check(self.L.lgca_b200_body_force(self.h, int(forcing), _ptr(draws), draws.size, C.byref(used), C.byref(rev)))
+        return int(used.value), int(rev.value)
+
+    def count_particles(self):
+        v = C.c_uint64(0)
+        self._check(self.L.lgca_b200_count_particles(self.h, C.byref(v)))
+        return int(v.value)
+
+    def init_random_device(self, seed=1):
+        self._check(self.L.lgca_b200_init_random_device(self.h, int(seed)))
+
+    def apply_bc_device(self, name):
+        self._check(self.L.lgca_b200_apply_bc_device(self.h, name.encode()))
+
+    def launch_count(self):
+        v = C.c_uint64(0)
+        self._check(self.L.lgca_b200_launch_count(self.h, C.byref(v)))
+        return int(v.value)
+
+    def info(self):
+        i = Info()
+        self._check(self.L.lgca_b200_get_info(self.h, C.byref(i)))
+        return i
+
+    def compute_stream(self):
+        return self.L.lgca_b200_compute_stream(self.h)
+
+    # --- multi-GPU halo plumbing (device pointers) -----------------------------------------------
+    def halo_bytes(self):
+        v = C.c_size_t(0)
+        self._check(self.L.lgca_b200_halo_bytes(self.h, C.byref(v)))
+        return int(v.value)
+
+    def halo_export(self, dev_top, dev_bottom):
+        self._check(self.L.lgca_b200_halo_export(self.h, C.c_void_p(dev_top), C.c_void_p(dev_bottom)))
+
+    def halo_import(self, dev_from_upper, dev_from_lower):
+        self._check(self.L.lgca_b200_halo_import(self.h, C.c_void_p(dev_from_upper), C.c_void_p(dev_from_lower)))

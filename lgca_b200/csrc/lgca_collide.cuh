@@ -1,0 +1,195 @@
+// Bit-sliced collision / wall rules of the four lattice-gas models, one machine word = 32 sites
+// (multi-spin coding).  Every function works on whole words; bit j of every word belongs to the same
+// lattice site.  Written once for device (LOP3 via inline PTX) and host (plain C++, used only by the
+// CPU unit test that checks these networks exhaustively against the oracle's truth tables).
+//
+// Reference semantics (paths relative to /root/reference):
+//   HPP      ModelDescriptor<HPP>::collide      src/lgca_models.h:134-152
+//   FHP-I    ModelDescriptor<FHP_I>::collide    src/lgca_models.h:367-395
+//   FHP-II   ModelDescriptor<FHP_II>::collide   src/lgca_models.h:568-613
+//   FHP-III  ModelDescriptor<FHP_III>::collide  src/lgca_models.h:786-856  (its extra terms :816-848
+//            are identically zero, so the table equals FHP-II's -- SURVEY.md fact 7 / A.3)
+//   walls    bounce_back / bounce_forward_x / bounce_forward_y, e.g. src/lgca_models.h:397-427
+//
+// The networks are NOT transcriptions of the reference's formulas: they are re-derived from the
+// collision table to minimise 3-input logic ops (the integer pipe is the co-limiter of this kernel):
+// a bit-sliced population count of the six movers classifies each site as "exactly 1/2/3 movers",
+// head-on pairs and symmetric triples are detected from that, and the rest-particle rules of FHP-II
+// collapse to "flip a trio of adjacent directions and the rest bit" around a centre direction.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define LGCA_HD __host__ __device__ __forceinline__
+#else
+#define LGCA_HD inline
+#endif
+
+namespace lgca_b200 {
+
+enum : int { MODEL_HPP = 0, MODEL_FHP_I = 1, MODEL_FHP_II = 2, MODEL_FHP_III = 3 };
+
+LGCA_HD constexpr int num_dir_of(int model) { return model == MODEL_HPP ? 4 : (model == MODEL_FHP_I ? 6 : 7); }
+// FHP-III as coded in the reference has FHP-II's table: both run the same network.
+LGCA_HD constexpr int rule_of(int model) { return model == MODEL_FHP_III ? MODEL_FHP_II : model; }
+
+// LOP3 truth-table operands: build a LUT as an expression of these, e.g. (TA & TB) | TC
+constexpr uint32_t TA = 0xF0, TB = 0xCC, TC = 0xAA;
+
+template <uint32_t LUT>
+LGCA_HD uint32_t lop3(uint32_t a, uint32_t b, uint32_t c)
+{
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(r) : "r"(a), "r"(b), "r"(c), "n"(LUT & 0xFF));
+    return r;
+#else
+    uint32_t r = 0;
+    for (int m = 0; m < 8; ++m) {
+        if (!((LUT >> m) & 1u)) continue;
+        uint32_t ta = (m & 4) ? a : ~a;
+        uint32_t tb = (m & 2) ? b : ~b;
+        uint32_t tc = (m & 1) ? c : ~c;
+        r |= ta & tb & tc;
+    }
+    return r;
+#endif
+}
+
+constexpr uint32_t LUT_XOR3 = TA ^ TB ^ TC;
+constexpr uint32_t LUT_MAJ  = (TA & TB) | (TA & TC) | (TB & TC);
+constexpr uint32_t LUT_OR3  = TA | TB | TC;
+constexpr uint32_t LUT_AND3 = TA & TB & TC;
+constexpr uint32_t LUT_MUX  = (TA & TB) | (~TA & TC);   // a ? b : c
+constexpr uint32_t LUT_XOR_OR = TA ^ (TB | TC);         // a ^ (b | c)
+
+// ---------------------------------------------------------------------------------------------
+// HPP: head-on pairs rotate by 90 degrees.  Changed states: 0101 <-> 1010, i.e. the four bits
+// alternate: (n0^n1)&(n1^n2)&(n2^n3).
+// ---------------------------------------------------------------------------------------------
+LGCA_HD void collide_hpp(uint32_t (&n)[7])
+{
+    uint32_t t = lop3<(TA ^ TB) & (TB ^ TC)>(n[0], n[1], n[2]);
+    uint32_t c = lop3<TA & (TB ^ TC)>(t, n[2], n[3]);
+    n[0] ^= c; n[1] ^= c; n[2] ^= c; n[3] ^= c;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FHP family.  Directions: 0=E 1=NE 2=NW 3=W 4=SW 5=SE (6=rest); i and i+3 are opposite.
+//   p = chirality word (frozen per-site random bit, src/omp_lattice.cpp:84,198):
+//   head-on pair (i,i+3), all other movers empty  -> rotates to (i+1,i+4) if p==0, (i-1,i+2) if p==1
+//   symmetric triple (0,2,4)<->(1,3,5)
+//   FHP-II: rest + single mover i            -> movers i-1,i+1 (rest consumed)
+//           movers i-1,i+1 only, no rest     -> mover i + rest
+// In change-mask form (out = in ^ ch), the pair (i, i+3) shares its head-on/triple mask T and the two
+// rest rules both flip the trio {c-1,c,c+1} plus the rest bit around a centre direction c.
+// ---------------------------------------------------------------------------------------------
+template <bool WITH_REST>
+LGCA_HD void collide_fhp(uint32_t (&n)[7], uint32_t p)
+{
+    // bit-sliced count of the six movers: cnt = s1 + s2 + 2*(c1 + c2)
+    const uint32_t s1 = lop3<LUT_XOR3>(n[0], n[1], n[2]);
+    const uint32_t c1 = lop3<LUT_MAJ>(n[0], n[1], n[2]);
+    const uint32_t s2 = lop3<LUT_XOR3>(n[3], n[4], n[5]);
+    const uint32_t c2 = lop3<LUT_MAJ>(n[3], n[4], n[5]);
+    const uint32_t cor = c1 | c2, cxr = c1 ^ c2;
+    // exactly two movers: (s1 & s2 & no carries) | (no ones & exactly one carry)
+    const uint32_t two_a = lop3<TA & TB & ~TC>(s1, s2, cor);
+    const uint32_t two_b = lop3<TA | (~TB & ~TC & 0xFF)>(two_a, s1, s2); // two_a | (~s1 & ~s2)
+    const uint32_t g2    = lop3<TA & (TB | TC)>(two_b, two_a, cxr);      // two_a | (~s1 & ~s2 & (c1^c2))
+    // head-on pairs
+    const uint32_t h1 = lop3<LUT_AND3>(n[1], n[4], g2); // dirs 1,4  (reference "db1")
+    const uint32_t h2 = lop3<LUT_AND3>(n[2], n[5], g2); // dirs 2,5  ("db2")
+    const uint32_t h3 = lop3<LUT_AND3>(n[0], n[3], g2); // dirs 3,0  ("db3")
+    // symmetric triples: the six movers alternate
+    const uint32_t u1  = lop3<(TA ^ TB) & (TB ^ TC)>(n[0], n[1], n[2]);
+    const uint32_t u2  = lop3<(TA ^ TB) & (TB ^ TC)>(n[2], n[3], n[4]);
+    const uint32_t u3  = lop3<TA & (TB ^ TC)>(u1, n[4], n[5]);
+    const uint32_t tri = u2 & u3;
+    // per-pair change masks: T14 = tri | h1 | (p ? h2 : h3), ...
+    uint32_t t14 = lop3<LUT_OR3>(tri, h1, lop3<LUT_MUX>(p, h2, h3));
+    uint32_t t25 = lop3<LUT_OR3>(tri, h2, lop3<LUT_MUX>(p, h3, h1));
+    uint32_t t30 = lop3<LUT_OR3>(tri, h3, lop3<LUT_MUX>(p, h1, h2));
+
+    if (WITH_REST) {
+        const uint32_t r   = n[6];
+        const uint32_t one = lop3<(TA ^ TB) & ~TC>(s1, s2, cor); // exactly one mover
+        const uint32_t H   = r & one;                            // rest + single mover
+        const uint32_t G   = g2 & ~r;                            // two movers, no rest
+        uint32_t cen[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const uint32_t t = lop3<LUT_AND3>(G, n[(i + 5) % 6], n[(i + 1) % 6]);
+            cen[i] = lop3<(TA & TB) | TC>(H, n[i], t);
+        }
+        const uint32_t chr = lop3<LUT_OR3>(cen[0], cen[1], cen[2]) | lop3<LUT_OR3>(cen[3], cen[4], cen[5]);
+        uint32_t o[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            const uint32_t R = lop3<LUT_OR3>(cen[(i + 5) % 6], cen[i], cen[(i + 1) % 6]);
+            const uint32_t T = (i == 1 || i == 4) ? t14 : ((i == 2 || i == 5) ? t25 : t30);
+            o[i] = lop3<LUT_XOR_OR>(n[i], T, R);
+        }
+#pragma unroll
+        for (int i = 0; i < 6; ++i) n[i] = o[i];
+        n[6] = r ^ chr;
+    } else {
+        n[1] ^= t14; n[4] ^= t14;
+        n[2] ^= t25; n[5] ^= t25;
+        n[3] ^= t30; n[0] ^= t30;
+    }
+}
+
+template <int MODEL>
+LGCA_HD void collide(uint32_t (&n)[7], uint32_t p)
+{
+    if (rule_of(MODEL) == MODEL_HPP) collide_hpp(n);
+    else if (rule_of(MODEL) == MODEL_FHP_I) collide_fhp<false>(n, p);
+    else collide_fhp<true>(n, p);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Direction permutations of the wall rules (src/lgca_models.h:44-48 HPP, :239-243 / :446-450 FHP)
+// ---------------------------------------------------------------------------------------------
+template <int MODEL> LGCA_HD constexpr int inv_dir(int d)
+{
+    return rule_of(MODEL) == MODEL_HPP ? ((d + 2) & 3) : (d == 6 ? 6 : (d + 3) % 6);
+}
+template <int MODEL> LGCA_HD constexpr int mir_x_dir(int d) // mirror at the x axis (N/S walls)
+{
+    return rule_of(MODEL) == MODEL_HPP ? ((4 - d) & 3) : (d == 6 ? 6 : (6 - d) % 6);
+}
+template <int MODEL> LGCA_HD constexpr int mir_y_dir(int d) // mirror at the y axis (E/W walls)
+{
+    return rule_of(MODEL) == MODEL_HPP ? ((d & 1) ? d : (d ^ 2)) : (d == 6 ? 6 : (9 - d) % 6);
+}
+
+// Collision + wall handling of one word of sites (SURVEY A.4 / src/omp_lattice.cpp:193-231):
+//   fluid      -> collide
+//   no-slip    -> out[d] = in[INV d]
+//   slip       -> MIR_Y on E/W edge columns, else MIR_X on N/S edge rows, else pass-through
+// `ns`/`sl` are the solid masks, `ew` the mask of sites on the E/W domain edge, `ns_row` all-ones when
+// the row is the northern or southern domain edge.
+template <int MODEL, bool HAS_NS, bool HAS_SL>
+LGCA_HD void collide_and_walls(uint32_t (&n)[7], uint32_t p, uint32_t ns, uint32_t sl, uint32_t ew, uint32_t ns_row)
+{
+    constexpr int ND = num_dir_of(MODEL);
+    uint32_t in[7];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) in[d] = n[d];
+    collide<MODEL>(n, p);
+    if (HAS_NS) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) n[d] = lop3<LUT_MUX>(ns, in[inv_dir<MODEL>(d)], n[d]);
+    }
+    if (HAS_SL) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) {
+            uint32_t s = lop3<LUT_MUX>(ns_row, in[mir_x_dir<MODEL>(d)], in[d]);
+            s          = lop3<LUT_MUX>(ew, in[mir_y_dir<MODEL>(d)], s);
+            n[d]       = lop3<LUT_MUX>(sl, s, n[d]);
+        }
+    }
+}
+
+} // namespace lgca_b200

@@ -1,0 +1,76 @@
+// Internal (library-private) declarations: the handle behind lgca_b200_lattice and the kernel
+// launchers implemented in the individual .cu files.
+#pragma once
+#include <stdint.h>
+#include <cuda_runtime.h>
+
+#include "../../include/lgca_b200.h"
+#include "lgca_common.cuh"
+
+struct lgca_b200_lattice {
+    lgca_b200_config cfg;
+    lgca_b200::Geom  g;
+    int              nd;          // NUM_DIR of the model
+    int              k_fuse;      // steps fused per pass by the wavefront kernel
+    uint32_t*        planes[2];   // ping-pong occupation planes [nd][rows][pitch]
+    int              cur;         // index of the live buffer
+    uint32_t*        snap;        // snapshot planes (copy_data_to_output_buffer)
+    uint32_t*        ns;          // no-slip solid mask plane  [rows][pitch]
+    uint32_t*        sl;          // slip solid mask plane
+    uint32_t*        ch;          // chirality plane
+    uint32_t*        xedge;       // [pitch] mask of the E/W domain-edge sites of a row
+    uint32_t*        d_flags;     // [2] device flags: any no-slip / any slip cell
+    int              has_ns, has_sl;
+    int              have_state, have_types, have_rnd;
+    cudaStream_t     s_compute, s_post;
+    cudaEvent_t      ev_snap, ev_post, ev_t0, ev_t1;
+    // staging (lazily allocated, reused)
+    void*            d_stage[2];
+    size_t           stage_bytes;
+    float*           d_cell_density;
+    float*           d_cell_momentum;
+    float*           d_mean_density;
+    float*           d_mean_momentum;
+    double*          d_scalars;   // small reduction scratch (device)
+    double*          h_scalars;   // pinned host mirror
+    int32_t*         d_draws;     // body-force scratch
+    uint8_t*         d_draw_bytes;
+    uint8_t*         h_draw_bytes;
+    size_t           draw_cap;
+    uint64_t         launches;
+    uint64_t         device_bytes;
+};
+
+namespace lgca_b200 {
+
+// lgca_step_simple.cu : one 32-site word per thread, one step per pass
+int launch_step_simple(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s);
+// lgca_step_wave.cu : register wavefront, k steps per HBM pass
+int launch_step_wave(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
+bool wave_supported(const lgca_b200_lattice* h, int k);
+
+// lgca_pack.cu : reference layouts <-> bit-planes
+int launch_pack_state(lgca_b200_lattice* h, const uint8_t* d_bytes, uint32_t* planes, uint32_t row0, uint32_t nrows,
+                      cudaStream_t s);
+int launch_unpack_state(lgca_b200_lattice* h, const uint32_t* planes, uint8_t* d_bytes, uint32_t row0, uint32_t nrows,
+                        cudaStream_t s);
+int launch_pack_cell_type(lgca_b200_lattice* h, const int32_t* d_ct, uint32_t row0, uint32_t nrows, cudaStream_t s);
+int launch_pack_rnd(lgca_b200_lattice* h, const uint8_t* d_bits, uint64_t first_bit, uint32_t row0, uint32_t nrows,
+                    cudaStream_t s);
+int launch_build_xedge(lgca_b200_lattice* h, cudaStream_t s);
+
+// lgca_post.cu : popcount reductions and field kernels
+int launch_cell_fields(lgca_b200_lattice* h, const uint32_t* planes, float* d_rho, float* d_mom, cudaStream_t s);
+int launch_mean_fields(lgca_b200_lattice* h, const uint32_t* planes, float* d_mrho, float* d_mmom, int exact,
+                       cudaStream_t s);
+int launch_mean_velocity(lgca_b200_lattice* h, const uint32_t* planes, double* d_out3, cudaStream_t s);
+int launch_count_particles(lgca_b200_lattice* h, const uint32_t* planes, unsigned long long* d_out, cudaStream_t s);
+int launch_gather_cells(lgca_b200_lattice* h, const uint32_t* planes, const int32_t* d_cells, size_t n, uint8_t* d_bytes,
+                        cudaStream_t s);
+int launch_apply_flips(lgca_b200_lattice* h, uint32_t* planes, const int32_t* d_cells, size_t n, cudaStream_t s);
+
+// lgca_init.cu : device-side synthetic initial data and BC painting
+int launch_init_random(lgca_b200_lattice* h, uint32_t* planes, uint64_t seed, cudaStream_t s);
+int launch_paint_bc(lgca_b200_lattice* h, int bc_kind, cudaStream_t s);
+
+} // namespace lgca_b200
