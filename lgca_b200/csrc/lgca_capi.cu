@@ -90,7 +90,7 @@ int lgca_b200_create(const lgca_b200_config* cfg, lgca_b200_lattice** out)
                            cfg->dim_x < 4 * cfg->cg_radius))
         return set_error(LGCA_B200_EINVAL, "dims must be multiples of 2*cg_radius and dim_x >= 4*cg_radius "
                                            "(reference: src/lattice.cpp:152-153)");
-    if (cfg->k_fuse < 0 || cfg->k_fuse > 8) return set_error(LGCA_B200_EINVAL, "k_fuse must be in [0, 8]");
+    if (cfg->k_fuse < 0 || cfg->k_fuse > LGCA_MAX_K) return set_error(LGCA_B200_EINVAL, "k_fuse must be in [0, %d]", LGCA_MAX_K);
 
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -109,7 +109,7 @@ int lgca_b200_create(const lgca_b200_config* cfg, lgca_b200_lattice** out)
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
     h->nd  = num_dir_of(cfg->model);
-    h->k_fuse = cfg->k_fuse ? cfg->k_fuse : 2;
+    h->k_fuse = cfg->k_fuse ? cfg->k_fuse : LGCA_MAX_K;
 
     const bool whole = (cfg->y_rows == 0 || cfg->y_rows == cfg->dim_y);
     if (!whole) {

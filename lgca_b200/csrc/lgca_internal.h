@@ -7,6 +7,18 @@
 #include "../../include/lgca_b200.h"
 #include "lgca_common.cuh"
 
+#define LGCA_MAX_K 4
+
+namespace lgca_b200 {
+// tiling of the wavefront kernel for one k (lgca_step_wave.cu)
+struct WavePlan {
+    int bands;      // 30-word bands per row
+    int chunk_rows; // output rows per chunk (even)
+    int chunks;     // chunks over the stored rows
+    int tiles;      // bands * chunks = warps launched
+};
+} // namespace lgca_b200
+
 struct lgca_b200_lattice {
     lgca_b200_config cfg;
     lgca_b200::Geom  g;
@@ -37,6 +49,8 @@ struct lgca_b200_lattice {
     uint8_t*         d_draw_bytes;
     uint8_t*         h_draw_bytes;
     size_t           draw_cap;
+    lgca_b200::WavePlan plans[LGCA_MAX_K + 1];
+    int              plan_valid[LGCA_MAX_K + 1];
     uint64_t         launches;
     uint64_t         device_bytes;
 };

@@ -14,8 +14,14 @@
 //   * Collision + walls are the LOP3 networks of lgca_collide.cuh.
 //   * Lanes 0 and 31 are halo lanes: every step invalidates one more bit at the band edges, so for
 //     K <= 32 the 30 interior words stay exact.  Chunks overlap by K rows at both ends (recomputed).
-//   * Periodic wrap: rows by index arithmetic; in x the edge lanes assemble their word from the
-//     periodic images (fetch_word), which also covers widths that are not multiples of 32.
+//   * Periodic wrap: rows by index arithmetic; in x the edge lanes read the periodic image of their
+//     word (resolved once per lane), which also covers widths that are not multiples of 32.
+//   * The next level-0 row and the level-1 masks are prefetched one iteration ahead; the pipeline
+//     fill (first 2K rows of a chunk) runs in a separate, predicated copy of the row body so that the
+//     steady-state loop is branch-free.
+#include <math.h>
+#include <stdlib.h>
+
 #include "lgca_internal.h"
 
 namespace lgca_b200 {
@@ -31,23 +37,145 @@ __device__ __forceinline__ uint32_t down1(uint32_t w) // site x <- site x+1
     return __funnelshift_r(w, __shfl_down_sync(0xFFFFFFFFu, w, 1), 1);
 }
 
-struct WaveParams {
-    int bands;          // bands per row
-    int chunk_rows;     // output rows per chunk (even)
-    int chunks;         // chunks per lattice
-    int tiles;          // bands * chunks
+// Per-lane view of the periodic row: where this lane's 32 sites come from.
+template <bool IRREG>
+struct LaneSrc {
+    int  wa, wb, sh, n1;
+    bool regular;
+    __device__ __forceinline__ uint32_t load(const uint32_t* __restrict__ row) const
+    {
+        uint32_t v = __ldg(row + wa);
+        if (IRREG) {
+            if (!regular) { // lanes at the row end of a width that is not a multiple of 32
+                v = __funnelshift_r(v, __ldg(row + wb), sh);
+                if (n1 < 32) v = (v & low_mask(n1)) | (__ldg(row) << n1);
+            }
+        }
+        return v;
+    }
 };
 
-template <int MODEL, int K, bool HAS_NS, bool HAS_SL>
+// Everything one lane carries through the row loop.
+template <int K>
+struct WaveState {
+    // delay lines of the level transition s-1 -> s (index s-1): planes of the previous row (C*) and
+    // planes 1,2 of the row before that (D*)
+    uint32_t C0[K], C1[K], C2[K], C3[K], C6[K], D1[K], D2[K];
+    uint32_t nxt[7];          // prefetched level-0 row
+    uint32_t m_p, m_ns, m_sl; // prefetched masks of the row that level 1 produces next
+    int      r0m;             // stored index of the level-0 row that arrived last
+};
+
+// One iteration: level-0 row r0 arrives, every level s produces its row r0 - s, and the level-K row
+// r0 - K is stored.  PAR = parity of the iteration index (compile time); WARM = pipeline still filling
+// (levels whose inputs are not there yet are skipped, nothing is stored before iteration 2K).
+template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG, int PAR, bool WARM>
+__device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>& src, int jc, int ya,
+                                         const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
+                                         const uint32_t* __restrict__ ns_p, const uint32_t* __restrict__ sl_p,
+                                         const uint32_t* __restrict__ ch_p, const Geom& g, uint32_t ew, bool store_lane,
+                                         uint32_t vmask, int wi)
+{
+    constexpr int  ND  = num_dir_of(MODEL);
+    constexpr bool HPP = rule_of(MODEL) == MODEL_HPP;
+    const int rows = (int)g.rows;
+
+    uint32_t a[7];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) a[d] = st.nxt[d];
+    // masks for level 1 (row r0 - 1) were prefetched during the previous iteration
+    const uint32_t p1 = st.m_p, ns1 = st.m_ns, sl1 = st.m_sl;
+
+    if (++st.r0m >= rows) st.r0m -= rows; // stored index of the arriving row r0
+    {
+        // prefetch the next level-0 row (r0 + 1) and the masks of row r0 (level 1 needs them next
+        // time).  Past the end of the chunk this reads a valid but unneeded row.
+        const int    rn = (st.r0m + 1 >= rows) ? st.r0m + 1 - rows : st.r0m + 1;
+        const size_t r  = (size_t)rn * g.pitch;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) st.nxt[d] = src.load(in + (size_t)d * g.plane_stride + r);
+        const size_t rm = (size_t)st.r0m * g.pitch;
+        if (!HPP) st.m_p = src.load(ch_p + rm);
+        if (HAS_NS) st.m_ns = src.load(ns_p + rm);
+        if (HAS_SL) st.m_sl = src.load(sl_p + rm);
+    }
+#pragma unroll
+    for (int s = 1; s <= K; ++s) {
+        // level s-1 row q = r0-(s-1) is in a[]; produce level s row y = q-1 = r0-s
+        uint32_t n[7];
+#pragma unroll
+        for (int d = 0; d < 7; ++d) n[d] = 0u;
+        if (!WARM || jc >= 2 * s) {
+            // ya is even and stored-row parity equals global parity (halo and y0 are even)
+            const bool odd = ((K + PAR + s) & 1) != 0;
+            if (HPP) {
+                n[0] = up1(st.C0[s - 1]);
+                n[2] = down1(st.C2[s - 1]);
+                n[1] = st.D1[s - 1];      // plane 1 of row y-1
+                n[3] = a[3];              // plane 3 of row y+1
+            } else {
+                n[0] = up1(st.C0[s - 1]);
+                n[3] = down1(st.C3[s - 1]);
+                if (ND == 7) n[6] = st.C6[s - 1];
+                if (!odd) {
+                    n[1] = up1(st.D1[s - 1]);
+                    n[2] = st.D2[s - 1];
+                    n[4] = a[4];
+                    n[5] = up1(a[5]);
+                } else {
+                    n[1] = st.D1[s - 1];
+                    n[2] = down1(st.D2[s - 1]);
+                    n[4] = down1(a[4]);
+                    n[5] = a[5];
+                }
+            }
+            int ym = st.r0m - s; // stored index of row r0 - s (rows >= 2K)
+            if (ym < 0) ym += rows;
+            uint32_t p = 0u, ns = 0u, sl = 0u;
+            if (s == 1) {
+                p = p1; ns = ns1; sl = sl1;
+            } else {
+                // deeper levels re-read their mask words (this lane loaded them s-1 iterations ago: L1 hits)
+                const size_t rm = (size_t)ym * g.pitch;
+                if (!HPP) p = src.load(ch_p + rm);
+                if (HAS_NS) ns = src.load(ns_p + rm);
+                if (HAS_SL) sl = src.load(sl_p + rm);
+            }
+            const uint32_t ns_row =
+                (HAS_SL && ((uint32_t)ym == g.row_south || (uint32_t)ym == g.row_north)) ? 0xFFFFFFFFu : 0u;
+            collide_and_walls<MODEL, HAS_NS, HAS_SL>(n, p, ns, sl, ew, ns_row);
+        }
+        // rotate the delay line of this level transition
+        st.D1[s - 1] = st.C1[s - 1];
+        st.C1[s - 1] = a[1];
+        st.C0[s - 1] = a[0];
+        if (HPP) {
+            st.C2[s - 1] = a[2];
+        } else {
+            st.D2[s - 1] = st.C2[s - 1];
+            st.C2[s - 1] = a[2];
+            st.C3[s - 1] = a[3];
+            if (ND == 7) st.C6[s - 1] = a[6];
+        }
+#pragma unroll
+        for (int d = 0; d < ND; ++d) a[d] = n[d];
+    }
+    if ((!WARM || jc >= 2 * K) && store_lane) {
+        const size_t ro = (size_t)(ya - 2 * K + jc) * g.pitch + wi;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) out[(size_t)d * g.plane_stride + ro] = IRREG ? (a[d] & vmask) : a[d];
+    }
+}
+
+template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
 __global__ void __launch_bounds__(128) step_wave_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
                                                         const uint32_t* __restrict__ ns_p,
                                                         const uint32_t* __restrict__ sl_p,
                                                         const uint32_t* __restrict__ ch_p,
                                                         const uint32_t* __restrict__ xedge, const Geom g,
-                                                        const WaveParams wp)
+                                                        const WavePlan wp)
 {
-    constexpr int  ND  = num_dir_of(MODEL);
-    constexpr bool HPP = rule_of(MODEL) == MODEL_HPP;
+    constexpr int ND = num_dir_of(MODEL);
     const int lane = threadIdx.x & 31;
     const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (tile >= wp.tiles) return;
@@ -57,135 +185,92 @@ __global__ void __launch_bounds__(128) step_wave_kernel(const uint32_t* __restri
     const int ya    = chunk * wp.chunk_rows;                 // first output row (even)
     const int yb    = min(ya + wp.chunk_rows, (int)g.rows);  // one past the last output row
     const int total = (yb - ya) + 2 * K;                     // level-0 rows to push through
+    const int rows  = (int)g.rows;
 
-    // plain in-row word or periodic image?
-    const bool regular = (wi >= 0) && (wi < (int)g.nw - (g.rem ? 1 : 0));
-    const bool store_lane = (lane >= 1) && (lane <= WAVE_VALID) && (wi < (int)g.nw);
-    const uint32_t vmask = store_lane ? valid_mask(g, wi) : 0u;
-    const uint32_t ew = HAS_SL ? fetch_word(xedge, wi, g) : 0u;
-
-    auto load = [&](const uint32_t* __restrict__ row) -> uint32_t {
-        return regular ? __ldg(row + wi) : fetch_word(row, wi, g);
-    };
-    const int rows = (int)g.rows;
-    // level-0 row index modulo the stored rows, advanced incrementally (no division in the loop)
-    int r0m = ya - K;
-    if (r0m < 0) r0m += rows;
-
-    // delay lines per level transition (level s-1 -> s uses index s-1)
-    uint32_t C0[K], C1[K], C2[K], C3[K], C6[K], D1[K], D2[K];
-#pragma unroll
-    for (int s = 0; s < K; ++s) { C0[s] = C1[s] = C2[s] = C3[s] = C6[s] = D1[s] = D2[s] = 0u; }
-
-    // software prefetch of the next level-0 row
-    uint32_t nxt[7];
-    {
-        const size_t r = (size_t)r0m * g.pitch;
-#pragma unroll
-        for (int d = 0; d < ND; ++d) nxt[d] = load(in + (size_t)d * g.plane_stride + r);
-    }
-    --r0m; // advanced to the arriving row at the top of every iteration
-
-    for (int j = 0; j < total; j += 2) {
-#pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-            const int jc = j + jj;
-            if (jc < total) {
-                uint32_t a[7];
-#pragma unroll
-                for (int d = 0; d < ND; ++d) a[d] = nxt[d];
-                const int r0 = ya - K + jc; // level-0 row that just arrived (unwrapped)
-                if (++r0m >= rows) r0m -= rows; // ... and its stored index
-                if (jc + 1 < total) {
-                    const int rn = (r0m + 1 >= rows) ? r0m + 1 - rows : r0m + 1;
-                    const size_t r = (size_t)rn * g.pitch;
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) nxt[d] = load(in + (size_t)d * g.plane_stride + r);
-                }
-#pragma unroll
-                for (int s = 1; s <= K; ++s) {
-                    // level s-1 row q = r0-(s-1) has arrived in a[]; produce level s row q-1 = r0-s
-                    uint32_t n[7];
-#pragma unroll
-                    for (int d = 0; d < 7; ++d) n[d] = 0u;
-                    if (jc >= 2 * s) {
-                        int ym = r0m - s;          // stored index of row r0 - s (needs rows >= K)
-                        if (ym < 0) ym += rows;
-                        // ya is even and stored-row parity equals global parity (halo is even)
-                        const bool odd = ((K + jj + s) & 1) != 0;
-                        if (HPP) {
-                            n[0] = up1(C0[s - 1]);
-                            n[2] = down1(C2[s - 1]);
-                            n[1] = D1[s - 1];       // plane 1 of row y-1
-                            n[3] = a[3];            // plane 3 of row y+1
-                        } else {
-                            n[0] = up1(C0[s - 1]);
-                            n[3] = down1(C3[s - 1]);
-                            if (ND == 7) n[6] = C6[s - 1];
-                            if (!odd) {
-                                n[1] = up1(D1[s - 1]);
-                                n[2] = D2[s - 1];
-                                n[4] = a[4];
-                                n[5] = up1(a[5]);
-                            } else {
-                                n[1] = D1[s - 1];
-                                n[2] = down1(D2[s - 1]);
-                                n[4] = down1(a[4]);
-                                n[5] = a[5];
-                            }
-                        }
-                        const size_t rm = (size_t)ym * g.pitch;
-                        const uint32_t p  = HPP ? 0u : load(ch_p + rm);
-                        const uint32_t ns = HAS_NS ? load(ns_p + rm) : 0u;
-                        const uint32_t sl = HAS_SL ? load(sl_p + rm) : 0u;
-                        const uint32_t ns_row =
-                            (HAS_SL && ((uint32_t)ym == g.row_south || (uint32_t)ym == g.row_north)) ? 0xFFFFFFFFu : 0u;
-                        collide_and_walls<MODEL, HAS_NS, HAS_SL>(n, p, ns, sl, ew, ns_row);
-                    }
-                    // rotate the delay line of this level transition
-                    if (HPP) {
-                        D1[s - 1] = C1[s - 1];      // plane 1: row q-1 -> becomes row y-1 next time
-                        C1[s - 1] = a[1];
-                        C0[s - 1] = a[0];
-                        C2[s - 1] = a[2];
-                    } else {
-                        D1[s - 1] = C1[s - 1];
-                        D2[s - 1] = C2[s - 1];
-                        C1[s - 1] = a[1];
-                        C2[s - 1] = a[2];
-                        C0[s - 1] = a[0];
-                        C3[s - 1] = a[3];
-                        if (ND == 7) C6[s - 1] = a[6];
-                    }
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) a[d] = n[d];
-                }
-                if (jc >= 2 * K && store_lane) {
-                    const size_t ro = (size_t)(r0 - K) * g.pitch + wi;
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) out[(size_t)d * g.plane_stride + ro] = a[d] & vmask;
-                }
-            }
+    // Periodic images in x are resolved ONCE per lane:
+    //   * width a multiple of 32: every lane reads one plain word at a wrapped index;
+    //   * otherwise lanes whose 32 sites touch the row end assemble them from up to three words
+    //     (two around bit position p, plus word 0 after the wrap) with precomputed indices/shifts.
+    LaneSrc<IRREG> src;
+    src.wa = wi; src.wb = 0; src.sh = 0; src.n1 = 32; src.regular = true;
+    if (!IRREG) {
+        if (src.wa < 0) src.wa += (int)g.nw;
+        else if (src.wa >= (int)g.nw) src.wa %= (int)g.nw;
+    } else {
+        src.regular = (wi >= 0) && (wi < (int)g.nw - 1);
+        if (!src.regular) {
+            long long p = ((long long)wi * 32) % (long long)g.dim_x;
+            if (p < 0) p += g.dim_x;
+            src.wa = (int)(p >> 5);
+            src.sh = (int)(p & 31);
+            src.wb = min(src.wa + 1, (int)g.nw - 1);
+            src.n1 = (int)min((long long)32, (long long)g.dim_x - p); // sites before the row end
         }
     }
+    const bool     store_lane = (lane >= 1) && (lane <= WAVE_VALID) && (wi < (int)g.nw);
+    const uint32_t vmask      = store_lane ? valid_mask(g, wi) : 0u;
+    const uint32_t ew         = HAS_SL ? src.load(xedge) : 0u;
+
+    WaveState<K> st;
+#pragma unroll
+    for (int s = 0; s < K; ++s) st.C0[s] = st.C1[s] = st.C2[s] = st.C3[s] = st.C6[s] = st.D1[s] = st.D2[s] = 0u;
+    st.m_p = st.m_ns = st.m_sl = 0u;
+    st.r0m = ya - K;
+    if (st.r0m < 0) st.r0m += rows;
+    {
+        const size_t r = (size_t)st.r0m * g.pitch;
+#pragma unroll
+        for (int d = 0; d < ND; ++d) st.nxt[d] = src.load(in + (size_t)d * g.plane_stride + r);
+#pragma unroll
+        for (int d = ND; d < 7; ++d) st.nxt[d] = 0u;
+    }
+    --st.r0m; // wave_row advances it to the arriving row first thing
+
+#define LGCA_ROW(PAR, WARM, JC)                                                                                      \
+    wave_row<MODEL, K, HAS_NS, HAS_SL, IRREG, PAR, WARM>(st, src, JC, ya, in, out, ns_p, sl_p, ch_p, g, ew, store_lane, \
+                                                        vmask, wi)
+    // pipeline fill: iterations 0 .. 2K-1 (2K is even, so parities alternate from 0)
+#pragma unroll 1
+    for (int j = 0; j < 2 * K; j += 2) {
+        LGCA_ROW(0, true, j);
+        LGCA_ROW(1, true, j + 1);
+    }
+    // steady state
+    int j = 2 * K;
+#pragma unroll 1
+    for (; j + 1 < total; j += 2) {
+        LGCA_ROW(0, false, j);
+        LGCA_ROW(1, false, j + 1);
+    }
+    if (j < total) LGCA_ROW(0, false, j); // odd number of rows (HPP lattices with odd height)
+#undef LGCA_ROW
 }
 
-static WaveParams plan(const lgca_b200_lattice* h, int k)
+// Chunk height: enough tiles to fill the machine, long enough to amortise the K-row pipeline fill.
+// Cost model per fused step: every tile runs (cr + k - 1) level-rows (the fill is trapezoidal); tiles run
+// in rounds of `resident` warps per SM; an SM with fewer than `saturate` warps is latency-bound and
+// modelled as proportionally slower.
+static WavePlan make_plan(const lgca_b200_lattice* h, int k)
 {
     const Geom& g = h->g;
-    WaveParams wp;
+    WavePlan wp;
     wp.bands = ((int)g.nw + WAVE_VALID - 1) / WAVE_VALID;
-    // enough tiles to fill 148 SMs with ~16 warps each, but chunks long enough to amortise the 2K-row overlap
-    const int target_tiles = 148 * 16;
-    int chunks = (target_tiles + wp.bands - 1) / wp.bands;
-    int rows = (int)g.rows;
-    int cr = (rows + chunks - 1) / chunks;
-    const int min_rows = 16 * k;
-    if (cr < min_rows) cr = min_rows;
-    static int env_cr = -1;
-    if (env_cr < 0) { const char* e = getenv("LGCA_B200_CHUNK_ROWS"); env_cr = e ? atoi(e) : 0; }
-    if (env_cr > 0) cr = env_cr;
-    cr = (cr + 1) & ~1;
+    const int rows = (int)g.rows;
+    const char* e_cr = getenv("LGCA_B200_CHUNK_ROWS");
+    const char* e_res = getenv("LGCA_B200_RESIDENT_WARPS");
+    const double resident = e_res ? atof(e_res) : 16.0, saturate = 12.0;
+    int    best_cr = (rows + 1) & ~1;
+    double best = 1e300;
+    for (int cr = 2 * k; cr <= rows + 1; cr += 2) {
+        const int    chunks = (rows + cr - 1) / cr;
+        const double w      = (double)chunks * wp.bands / 148.0; // warps per SM
+        const double rounds = fmax(1.0, ceil(w / resident));
+        const double eff    = fmin(1.0, (w / rounds) / saturate);
+        const double cost   = (double)(cr + k - 1) * rounds / eff;
+        if (cost <= best) { best = cost; best_cr = cr; }
+    }
+    int cr = best_cr;
+    if (e_cr && atoi(e_cr) > 0) cr = (atoi(e_cr) + 1) & ~1;
     if (cr > rows) cr = (rows + 1) & ~1;
     wp.chunk_rows = cr;
     wp.chunks = (rows + cr - 1) / cr;
@@ -195,10 +280,11 @@ static WaveParams plan(const lgca_b200_lattice* h, int k)
 
 bool wave_supported(const lgca_b200_lattice* h, int k)
 {
-    if (k < 1 || k > 4) return false;
-    // strips keep an even halo so that stored-row parity equals global parity
+    if (k < 1 || k > LGCA_MAX_K) return false;
+    // strips keep an even halo and start on an even row so that stored-row parity equals global parity
     if ((h->g.halo & 1u) || (h->g.y0 & 1u)) return false;
     if (h->g.rows < 8 || (int)h->g.rows < 2 * k) return false;
+    if (h->g.dim_x < 64) return false; // tiny rows wrap more than once inside a word: generic kernel
     if (!h->g.wrap_y && (uint32_t)k > h->g.halo) return false;
     return true;
 }
@@ -206,12 +292,19 @@ bool wave_supported(const lgca_b200_lattice* h, int k)
 template <int MODEL, int K>
 static int launch_mk(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s)
 {
-    const WaveParams wp = plan(h, K);
+    if (!h->plan_valid[K]) { h->plans[K] = make_plan(h, K); h->plan_valid[K] = 1; }
+    const WavePlan wp = h->plans[K];
     const int warps_per_block = 4;
     dim3 block(32 * warps_per_block, 1, 1);
     dim3 grid((wp.tiles + warps_per_block - 1) / warps_per_block, 1, 1);
-#define GO(NS, SL)                                                                                              \
-    step_wave_kernel<MODEL, K, NS, SL><<<grid, block, 0, s>>>(in, out, h->ns, h->sl, h->ch, h->xedge, h->g, wp)
+    const bool irreg = h->g.rem != 0;
+#define GO(NS, SL)                                                                                                \
+    do {                                                                                                          \
+        if (irreg) step_wave_kernel<MODEL, K, NS, SL, true><<<grid, block, 0, s>>>(in, out, h->ns, h->sl, h->ch,  \
+                                                                                    h->xedge, h->g, wp);          \
+        else step_wave_kernel<MODEL, K, NS, SL, false><<<grid, block, 0, s>>>(in, out, h->ns, h->sl, h->ch,       \
+                                                                               h->xedge, h->g, wp);               \
+    } while (0)
     if (h->has_sl) { if (h->has_ns) GO(true, true); else GO(false, true); }
     else           { if (h->has_ns) GO(true, false); else GO(false, false); }
 #undef GO

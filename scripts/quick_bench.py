@@ -1,5 +1,6 @@
 """Quick device-side timing of the stepping kernels (development helper, not the bench contract)."""
-import sys, time
+import os, sys, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lgca_b200
 
 def run(model, dx, dy, bc, k_fuse=0, flags=0, steps=50, reps=3):
