@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the LGCA hot path on B200 (site updates per second).
+
+Contract:  python bench.py --gpus N --steps K --warmup W [--impl reference] [--workload periodic|karman]
+For N > 1 launch under torchrun (one rank per GPU); rank 0 prints ONE JSON line.
+
+Workload (BASELINE.json metric "FHP-III site updates/s at 1/2/4/8 B200"): config C5,
+lgca-periodic FHP-III, 32768 x 32768 sites PER GPU stacked in y (weak scaling, row strips, halo ring),
+all-fluid periodic torus, occupancy P = 1/7, chirality P = 1/2 generated on the device from a
+counter-based hash.  One bench "step" = 100 lattice updates (k-step temporal blocking
+inside) followed by the coarse-grained post-process of the snapshot and the device->host read of the
+coarse fields (C5: "coarse-grained output every 100 steps").  `--workload karman` runs config C3
+(FHP-III 16384 x 8192, walls + cylinder) instead; its N=1 numbers are also attached to the default line
+under "karman".
+
+value    : whole-job site updates/s with the lattice resident in HBM (CUDA events, max over ranks).
+e2e      : the same metric through the reference-facing call sequence with HOST buffers:
+           copy_data_to_device (pinned reference-layout state bytes) -> 100 x collide_and_propagate ->
+           snapshot + post_process (coarse fields to host) -> copy_data_from_device, per step.
+roofline : dominant kernel = step_wave_kernel (k fused steps per launch); algorithmic bytes per launch =
+           sites * (2*NUM_DIR + mask planes)/8 * k, divided by the average launch duration measured with
+           CUDA events on the engine's compute stream; peak = MEASURED_PEAKS.json hbm_gbs (burst copy).
+           With k-step temporal blocking real DRAM traffic is 1/k of the algorithmic bytes, so frac may
+           exceed 1; `traffic` is the ncu dram bytes per launch from profiles/.
+cpu_baseline / --impl reference : the UNMODIFIED reference OMP path (oracle/_ref, built from
+           /root/reference by oracle/Makefile) on all host cores, on a bounded sample of the workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+UPDATES_PER_STEP = 100
+WORKLOADS = {
+    # name: (model, dim_x, rows per GPU, bc, cg_radius, description)
+    "periodic": ("FHP_III", 32768, 32768, "periodic", 16,
+                 "lgca-periodic FHP-III 32768x32768 per GPU (BASELINE config C5), weak scaling in y"),
+    "karman": ("FHP_III", 16384, 8192, "karman", 16,
+               "lgca-karman FHP-III 16384x8192, pipe walls + cylinder, x-periodic (BASELINE config C3)"),
+}
+CPU_SAMPLE = {"periodic": (4096, 4096), "karman": (4096, 2048)}
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock, power and throttle reasons DURING the timed region (NVML, 20 ms period)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.stop_flag, self.err = index, [], False, None
+
+    def run(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            while not self.stop_flag:
+                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                                     int(get_reasons(h))))
+                time.sleep(0.02)
+        except Exception as ex:  # pragma: no cover
+            self.err = repr(ex)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml unavailable: %s" % self.err]}
+        # NVML clocks-event-reason bits
+        bits = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
+        sm = sorted(s[0] for s in self.samples)
+        seen = 0
+        for s_ in self.samples:
+            seen |= s_[2]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_sm, "power_w_max": max(s_[1] for s_ in self.samples),
+                "reasons": sorted(v for b_, v in bits.items() if seen & b_), "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's own OMP path on the host cores
+# ------------------------------------------------------------------------------------------------------
+def reference_setup(workload):
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import cpu_checkers as cc
+    model, _, _, bc, cg, _ = WORKLOADS[workload]
+    dx, dy = CPU_SAMPLE[workload]
+    cores = os.cpu_count() or 1
+    if cc.ref_available():
+        kind = "reference"
+        cc._ref_lib().lgca_ref_set_threads(1)  # deterministic construction (rand() inside omp loops)
+        if workload == "periodic":
+            lat = cc.Ref(model, "periodic", dx - 1, 0.2, cg, threads=1)
+        else:
+            lat = cc.Ref(model, "periodic", dx - 1, 0.2, cg, threads=1, dims=(dx, dy))
+        lat.apply_bc(bc)
+        lat.init("random")
+        lat.set_threads(cores)
+    else:  # the plain-C port (same algorithm, OpenMP over cells)
+        kind = "port"
+        lat = cc.Oracle(model, dims=(dx, dy), cg=cg)
+        lat.apply_bc(bc)
+        lat.init("random")
+    return lat, kind, cores, (dx, dy)
+
+
+def time_reference(workload, updates, warm=1):
+    lat, kind, cores, (dx, dy) = reference_setup(workload)
+    lat.step(warm)
+    t0 = time.perf_counter()
+    lat.step(updates)
+    dt = time.perf_counter() - t0
+    val = dx * dy * updates / dt
+    sample = "%s %dx%d %s, %d updates after %d warm-up (%.1f s)" % (WORKLOADS[workload][0], dx, dy, WORKLOADS[workload][3],
+                                                                      updates, warm, dt)
+    return val, dt, {"value": val, "unit": "site updates/s", "cores": cores, "kind": kind, "sample": sample}
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    model, dx, rows, bc, cg, desc = WORKLOADS[args.workload]
+    ups = 2  # lattice updates of the bounded sample per "step"
+    lat, kind, cores, (sx, sy) = reference_setup(args.workload)
+    for _ in range(args.warmup):
+        lat.step(ups)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        lat.step(ups)
+    dt = time.perf_counter() - t0
+    val = sx * sy * ups * args.steps / dt
+    line = {
+        "impl": "reference", "metric": "FHP-III site updates/s", "value": val, "unit": "site updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8 (byte per cell, bit per direction)",
+        "data": "synthetic",
+        "config": {"workload": desc, "global_lattice": [dx, rows * args.gpus],
+                   "note": "reference CPU path (OMP_Lattice::collide_and_propagate) on host cores; each step = %d updates of a "
+                           "bounded %dx%d sample of the workload (same model/BC/init)" % (ups, sx, sy)},
+        "cpu_baseline": {"value": val, "unit": "site updates/s", "cores": cores, "kind": kind,
+                         "sample": "%s %dx%d %s, %d steps x %d updates" % (model, sx, sy, bc, args.steps, ups)},
+        "e2e": {"value": val, "unit": "site updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------------------------------
+# the B200 arm
+# ------------------------------------------------------------------------------------------------------
+def build_engine(workload, rank, world, local_rank, k_fuse):
+    import lgca_b200
+    from lgca_b200.ring import partition_rows
+    model, dx, rows, bc, cg, _ = WORKLOADS[workload]
+    dim_y = rows * world
+    if world == 1:
+        e = lgca_b200.Engine(model, dx, dim_y, cg_radius=cg, bf_dir="x" if workload == "karman" else 0, device=local_rank,
+                             k_fuse=k_fuse, flags=lgca_b200.capi.FLAG_NO_CELL_FIELDS)
+    else:
+        y0, yr = partition_rows(dim_y, world, 2 * cg)[rank]
+        e = lgca_b200.Engine(model, dx, dim_y, cg_radius=cg, device=local_rank, k_fuse=k_fuse, y_begin=y0, y_rows=yr,
+                             flags=lgca_b200.capi.FLAG_NO_CELL_FIELDS)
+    e.apply_bc_device(bc)
+    e.init_random_device(seed=1)
+    return e
+
+
+def bench_step(ring, e, coarse_out):
+    """One bench step with the lattice resident in HBM: 100 updates + coarse post-process + read-back."""
+    ring.step(UPDATES_PER_STEP)
+    e.snapshot()
+    e.post_process(cell=False, mean=True, exact=False, out=coarse_out)
+
+
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    import lgca_b200
+    from lgca_b200.ring import Ring
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py --gpus %d must be launched with torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: lgca_b200 has no CPU path")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    model, dx, rows, bc, cg, desc = WORKLOADS[args.workload]
+    sites_rank = dx * rows
+    sites_total = sites_rank * world
+    e = build_engine(args.workload, rank, world, local_rank, args.k_fuse)
+    ring = Ring(e, rank, world, device=device)
+    info = e.info()
+    particles0 = e.count_particles()
+    coarse = {}
+
+    def barrier():
+        e.sync()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- device-resident throughput ----------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        bench_step(ring, e, coarse)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    stream = torch.cuda.ExternalStream(e.compute_stream(), device=device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = e.launch_count()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        bench_step(ring, e, coarse)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = e.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join(2)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = sites_total * UPDATES_PER_STEP * args.steps / (ms * 1e-3)
+
+    # ---- end to end through host buffers -----------------------------------------------------------------
+    host_state = lgca_b200.capi.PinnedArray((sites_rank,), "uint8")
+    e.download(host_state.array)
+    e2e_steps = max(1, min(args.steps, 3))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e.upload(state=host_state.array)             # copy_data_to_device()
+        if world > 1:
+            ring.exchange(Ring.STATE)                # ghost rows of the freshly uploaded strip
+        ring.step(UPDATES_PER_STEP)                  # 100 x collide_and_propagate()
+        e.snapshot()                                 # copy_data_to_output_buffer()
+        e.post_process(cell=False, mean=True, exact=False, out=coarse)  # post_process() -> host coarse fields
+        e.download(host_state.array)                 # copy_data_from_device()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([e2e_s], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = sites_total * UPDATES_PER_STEP * e2e_steps / e2e_s
+    coarse_bytes = sum(v.nbytes for v in coarse.values())
+    host_state.free()
+
+    # ---- mass conservation over the whole job (global particle count) ---------------------------------------
+    particles1 = e.count_particles()
+    if world > 1:
+        t = torch.tensor([particles0, particles1], device=device, dtype=torch.int64)
+        dist.all_reduce(t)
+        particles0, particles1 = int(t[0].item()), int(t[1].item())
+    conserved = particles0 == particles1
+
+    # ---- dominant kernel: average launch duration of the fused-step kernel, CUDA events on its stream ------
+    # (last: on a strip this skips the halo exchange and leaves the edge rows stale)
+    k = info.k_fuse
+    e.sync()
+    e.timed_kernel(5)
+    kms = min(e.timed_kernel(25) for _ in range(3))
+    alg_bytes = sites_rank * info.bytes_per_site_step_x8 / 8.0 * k
+    peak, peak_src = measured_peak()
+    achieved = alg_bytes / (kms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("%s_k%d" % (args.workload, k))
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "step_wave_kernel<FHP_II rule, K=%d>" % k,
+                "launch_ms": kms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "note": "algorithmic bytes = sites*(2*NUM_DIR+masks)/8 per step x k fused steps per launch; "
+                        "real DRAM traffic is ~1/k of it (temporal blocking), so frac can exceed 1"}
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "FHP-III site updates/s", "value": value, "unit": "site updates/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes (1 bit per site and direction)",
+            "data": "synthetic",
+            "config": {"workload": desc, "global_lattice": [dx, rows * world], "sites_per_gpu": sites_rank,
+                       "updates_per_step": UPDATES_PER_STEP, "k_fuse": k, "parallelism": "row strips x%d, halo ring" % world,
+                       "cache": "inputs larger than L2 (%.0f MB of bit-planes per GPU vs 126 MB L2)" % (
+                           sites_rank * info.num_planes / 8 / 1e6) if sites_rank * info.num_planes / 8 > 200e6 else
+                       "lattice (%.0f MB) is L2-resident" % (sites_rank * info.num_planes / 8 / 1e6),
+                       "step": "100 updates + snapshot + coarse post-process + D2H of coarse fields"},
+            "roofline": roofline,
+            "e2e": {"value": e2e_value, "unit": "site updates/s", "h2d_bytes_per_step": sites_rank * world,
+                    "d2h_bytes_per_step": (sites_rank + coarse_bytes) * world, "steps": e2e_steps,
+                    "path": "upload(pinned state bytes) -> 100 steps -> snapshot+post_process -> download"},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "particles_conserved": bool(conserved),
+        }
+    # ---- extras on rank 0 at N=1: CPU baseline and the Karman (C3) measurement ----------------------------
+    if world == 1 and line is not None:
+        if not args.no_cpu_baseline:
+            try:
+                _, _, cb = time_reference(args.workload, updates=args.cpu_updates)
+                line["cpu_baseline"] = cb
+            except Exception as ex:  # the checker is optional for the measurement itself
+                line["cpu_baseline"] = {"value": None, "unit": "site updates/s", "cores": os.cpu_count(), "kind": "unavailable",
+                                        "sample": repr(ex)}
+        if args.workload == "periodic" and not args.no_karman:
+            e.close()
+            line["karman"] = karman_extra(args, peak)
+    if line is not None:
+        print(json.dumps(line))
+    e.close()
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def karman_extra(args, peak):
+    """Config C3 on one GPU: device-resident throughput and kernel roofline (attached to the default line)."""
+    e = build_engine("karman", 0, 1, int(os.environ.get("LOCAL_RANK", "0")), args.k_fuse)
+    model, dx, rows, bc, cg, desc = WORKLOADS["karman"]
+    info = e.info()
+    k = info.k_fuse
+    e.timed_steps(k * 50)
+    ms = min(e.timed_steps(k * 100) for _ in range(3)) / 100
+    alg = dx * rows * info.bytes_per_site_step_x8 / 8.0 * k
+    out = {"workload": desc, "value": dx * rows * k / (ms * 1e-3), "unit": "site updates/s", "k_fuse": k, "launch_ms": ms,
+           "roofline_achieved_gbs": alg / (ms * 1e-3) / 1e9, "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak,
+           "cache": "bit-planes 117 MB: partly L2-resident"}
+    e.close()
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="periodic", choices=sorted(WORKLOADS))
+    ap.add_argument("--k-fuse", type=int, default=0)
+    ap.add_argument("--cpu-updates", type=int, default=12, help="updates of the bounded CPU sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-karman", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    return run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -144,6 +144,10 @@ int  lgca_b200_sync(lgca_b200_lattice* h);
 void* lgca_b200_compute_stream(lgca_b200_lattice* h);
 /* Runs n_steps updates bracketed by CUDA events on the compute stream; returns the elapsed device time. */
 int  lgca_b200_timed_steps(lgca_b200_lattice* h, int n_steps, float* elapsed_ms);
+/* Diagnostic for the roofline: `launches` back-to-back launches of the fused-step kernel (k_fuse steps each)
+ * bracketed by CUDA events on the compute stream; returns the average launch duration.  On a row strip this
+ * deliberately skips the halo exchange, so the strip's edge rows are stale afterwards (timing only). */
+int  lgca_b200_timed_kernel(lgca_b200_lattice* h, int launches, float* ms_per_launch);
 /* Kernel launches issued by this handle so far (bench.py's gpu_launches claim). */
 int  lgca_b200_launch_count(lgca_b200_lattice* h, uint64_t* out);
 
@@ -160,13 +164,24 @@ typedef struct {
 int  lgca_b200_get_info(lgca_b200_lattice* h, lgca_b200_info* out);
 
 /* ---- multi-GPU row strips (one handle per GPU / process) ----
- * Each strip keeps `halo` ghost rows above and below its own rows.  After every block of k fused steps
- * the owner exports its k top and k bottom rows and imports its neighbours' (periodic ring in y, like
- * the reference's always-periodic torus, src/omp_lattice.cpp:150-176).  The buffers are DEVICE
- * pointers (packed bit-plane rows) so the caller moves them with NCCL send/recv or CUDA P2P copies. */
-int  lgca_b200_halo_bytes(lgca_b200_lattice* h, size_t* bytes_per_side);
-int  lgca_b200_halo_export(lgca_b200_lattice* h, void* dev_top_rows, void* dev_bottom_rows);
-int  lgca_b200_halo_import(lgca_b200_lattice* h, const void* dev_from_upper, const void* dev_from_lower);
+ * The reference has no domain decomposition (single address space); this is the
+ * B200-native extension.  Each strip keeps `halo` ghost rows above and below its own rows (halo = k_fuse
+ * rounded up to even).  After every block of <= halo steps the owner exports its top and bottom `halo`
+ * own rows and imports its ring neighbours' (periodic in y, like the reference's always-periodic torus,
+ * src/omp_lattice.cpp:150-176).  Buffers are DEVICE pointers to packed rows ([plane][halo row][pitch
+ * words]); the caller moves them between GPUs (NCCL send/recv, CUDA P2P).  Both calls are asynchronous
+ * on the compute stream (lgca_b200_compute_stream) so the exchange can be stream-ordered without host
+ * synchronisation.  `what` selects the occupation planes or the three static mask planes (no-slip,
+ * slip, chirality), which are exchanged once after an upload from the host. */
+enum { LGCA_B200_HALO_STATE = 0, LGCA_B200_HALO_MASKS = 1 };
+int  lgca_b200_halo_rows(lgca_b200_lattice* h, uint32_t* rows);
+int  lgca_b200_halo_bytes(lgca_b200_lattice* h, int what, size_t* bytes_per_side);
+int  lgca_b200_halo_export(lgca_b200_lattice* h, int what, void* dev_top_rows, void* dev_bottom_rows);
+int  lgca_b200_halo_import(lgca_b200_lattice* h, int what, const void* dev_from_upper, const void* dev_from_lower);
+/* Wall-kind flags select the kernel variant.  With row strips every rank must run with the UNION of all
+ * strips' flags (a strip without walls of its own may import wall cells into its halo rows). */
+int  lgca_b200_get_wall_flags(lgca_b200_lattice* h, uint32_t* has_no_slip, uint32_t* has_slip);
+int  lgca_b200_set_wall_flags(lgca_b200_lattice* h, uint32_t has_no_slip, uint32_t has_slip);
 
 #ifdef __cplusplus
 }

@@ -19,8 +19,9 @@ SYMBOLS = [
     "lgca_b200_download", "lgca_b200_step", "lgca_b200_snapshot", "lgca_b200_post_process",
     "lgca_b200_mean_velocity", "lgca_b200_body_force", "lgca_b200_count_particles",
     "lgca_b200_init_random_device", "lgca_b200_apply_bc_device", "lgca_b200_sync",
-    "lgca_b200_compute_stream", "lgca_b200_timed_steps", "lgca_b200_launch_count", "lgca_b200_get_info",
-    "lgca_b200_halo_bytes", "lgca_b200_halo_export", "lgca_b200_halo_import",
+    "lgca_b200_compute_stream", "lgca_b200_timed_steps", "lgca_b200_timed_kernel", "lgca_b200_launch_count", "lgca_b200_get_info",
+    "lgca_b200_halo_rows", "lgca_b200_halo_bytes", "lgca_b200_halo_export", "lgca_b200_halo_import",
+    "lgca_b200_get_wall_flags", "lgca_b200_set_wall_flags",
 ]
 
 
@@ -78,11 +79,15 @@ def load_library():
     L.lgca_b200_compute_stream.argtypes = [vp]
     L.lgca_b200_compute_stream.restype = vp
     L.lgca_b200_timed_steps.argtypes = [vp, i32, C.POINTER(C.c_float)]
+    L.lgca_b200_timed_kernel.argtypes = [vp, i32, C.POINTER(C.c_float)]
     L.lgca_b200_launch_count.argtypes = [vp, C.POINTER(u64)]
     L.lgca_b200_get_info.argtypes = [vp, C.POINTER(Info)]
-    L.lgca_b200_halo_bytes.argtypes = [vp, C.POINTER(C.c_size_t)]
-    L.lgca_b200_halo_export.argtypes = [vp, vp, vp]
-    L.lgca_b200_halo_import.argtypes = [vp, vp, vp]
+    L.lgca_b200_halo_rows.argtypes = [vp, C.POINTER(C.c_uint32)]
+    L.lgca_b200_halo_bytes.argtypes = [vp, i32, C.POINTER(C.c_size_t)]
+    L.lgca_b200_halo_export.argtypes = [vp, i32, vp, vp]
+    L.lgca_b200_halo_import.argtypes = [vp, i32, vp, vp]
+    L.lgca_b200_get_wall_flags.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    L.lgca_b200_set_wall_flags.argtypes = [vp, C.c_uint32, C.c_uint32]
     _LIB = L
     return L
 
@@ -174,6 +179,11 @@ class Engine:
         self._check(self.L.lgca_b200_timed_steps(self.h, int(n), C.byref(ms)))
         return float(ms.value)
 
+    def timed_kernel(self, launches):
+        ms = C.c_float(0)
+        self._check(self.L.lgca_b200_timed_kernel(self.h, int(launches), C.byref(ms)))
+        return float(ms.value)
+
     def sync(self):
         self._check(self.L.lgca_b200_sync(self.h))
 
@@ -230,14 +240,29 @@ class Engine:
     def compute_stream(self):
         return self.L.lgca_b200_compute_stream(self.h)
 
-    # --- multi-GPU halo plumbing (device pointers) -----------------------------------------------
-    def halo_bytes(self):
-        v = C.c_size_t(0)
-        self._check(self.L.lgca_b200_halo_bytes(self.h, C.byref(v)))
+    # --- multi-GPU halo plumbing (device pointers; async on the compute stream) -------------------
+    HALO_STATE, HALO_MASKS = 0, 1
+
+    def halo_rows(self):
+        v = C.c_uint32(0)
+        self._check(self.L.lgca_b200_halo_rows(self.h, C.byref(v)))
         return int(v.value)
 
-    def halo_export(self, dev_top, dev_bottom):
-        self._check(self.L.lgca_b200_halo_export(self.h, C.c_void_p(dev_top), C.c_void_p(dev_bottom)))
+    def halo_bytes(self, what=0):
+        v = C.c_size_t(0)
+        self._check(self.L.lgca_b200_halo_bytes(self.h, what, C.byref(v)))
+        return int(v.value)
 
-    def halo_import(self, dev_from_upper, dev_from_lower):
-        self._check(self.L.lgca_b200_halo_import(self.h, C.c_void_p(dev_from_upper), C.c_void_p(dev_from_lower)))
+    def halo_export(self, what, dev_top, dev_bottom):
+        self._check(self.L.lgca_b200_halo_export(self.h, what, C.c_void_p(dev_top), C.c_void_p(dev_bottom)))
+
+    def halo_import(self, what, dev_from_upper, dev_from_lower):
+        self._check(self.L.lgca_b200_halo_import(self.h, what, C.c_void_p(dev_from_upper), C.c_void_p(dev_from_lower)))
+
+    def wall_flags(self):
+        a, b = C.c_uint32(0), C.c_uint32(0)
+        self._check(self.L.lgca_b200_get_wall_flags(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def set_wall_flags(self, has_no_slip, has_slip):
+        self._check(self.L.lgca_b200_set_wall_flags(self.h, int(has_no_slip), int(has_slip)))

@@ -280,11 +280,11 @@ int lgca_b200_download(lgca_b200_lattice* h, uint8_t* state)
     return 0;
 }
 
-int lgca_b200_step(lgca_b200_lattice* h, int n_steps)
+static int step_impl(lgca_b200_lattice* h, int n_steps, bool check_halo)
 {
     if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
     if (n_steps < 0) return set_error(LGCA_B200_EINVAL, "n_steps < 0");
-    if (h->g.halo && (uint32_t)n_steps > h->g.halo)
+    if (check_halo && h->g.halo && (uint32_t)n_steps > h->g.halo)
         return set_error(LGCA_B200_ESTATE, "a strip can advance at most halo=%u steps between halo exchanges", h->g.halo);
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     const bool simple = (h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) != 0;
@@ -304,6 +304,8 @@ int lgca_b200_step(lgca_b200_lattice* h, int n_steps)
     }
     return 0;
 }
+
+int lgca_b200_step(lgca_b200_lattice* h, int n_steps) { return step_impl(h, n_steps, true); }
 
 int lgca_b200_snapshot(lgca_b200_lattice* h)
 {
@@ -530,6 +532,23 @@ int lgca_b200_timed_steps(lgca_b200_lattice* h, int n_steps, float* elapsed_ms)
     return 0;
 }
 
+int lgca_b200_timed_kernel(lgca_b200_lattice* h, int launches, float* ms_per_launch)
+{
+    if (!h || !ms_per_launch || launches <= 0) return set_error(LGCA_B200_EINVAL, "bad argument");
+    LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+    int k = h->k_fuse;
+    while (k > 1 && !wave_supported(h, k)) --k;
+    LGCA_CUDA_CHECK(cudaEventRecord(h->ev_t0, h->s_compute));
+    int rc = step_impl(h, k * launches, false);
+    if (rc) return rc;
+    LGCA_CUDA_CHECK(cudaEventRecord(h->ev_t1, h->s_compute));
+    LGCA_CUDA_CHECK(cudaEventSynchronize(h->ev_t1));
+    float ms = 0;
+    LGCA_CUDA_CHECK(cudaEventElapsedTime(&ms, h->ev_t0, h->ev_t1));
+    *ms_per_launch = ms / launches;
+    return 0;
+}
+
 int lgca_b200_launch_count(lgca_b200_lattice* h, uint64_t* out)
 {
     if (!h || !out) return set_error(LGCA_B200_EINVAL, "null argument");
@@ -552,20 +571,34 @@ int lgca_b200_get_info(lgca_b200_lattice* h, lgca_b200_info* out)
     return 0;
 }
 
-int lgca_b200_halo_bytes(lgca_b200_lattice* h, size_t* bytes_per_side)
+int lgca_b200_halo_rows(lgca_b200_lattice* h, uint32_t* rows)
+{
+    if (!h || !rows) return set_error(LGCA_B200_EINVAL, "null argument");
+    *rows = h->g.halo;
+    return 0;
+}
+
+static int halo_planes(const lgca_b200_lattice* h, int what) { return what == LGCA_B200_HALO_STATE ? h->nd : 3; }
+
+int lgca_b200_halo_bytes(lgca_b200_lattice* h, int what, size_t* bytes_per_side)
 {
     if (!h || !bytes_per_side) return set_error(LGCA_B200_EINVAL, "null argument");
-    *bytes_per_side = (size_t)h->g.halo * h->g.pitch * sizeof(uint32_t) * h->nd;
+    if (what != LGCA_B200_HALO_STATE && what != LGCA_B200_HALO_MASKS) return set_error(LGCA_B200_EINVAL, "bad halo kind");
+    *bytes_per_side = (size_t)h->g.halo * h->g.pitch * sizeof(uint32_t) * halo_planes(h, what);
     return 0;
 }
 
 // packed halo layout: [plane][halo row][pitch words]
-static int halo_copy(lgca_b200_lattice* h, void* packed, uint32_t first_row, bool to_packed)
+static int halo_copy(lgca_b200_lattice* h, int what, void* packed, uint32_t first_row, bool to_packed)
 {
     const Geom& g = h->g;
     const size_t row_bytes = (size_t)g.pitch * sizeof(uint32_t);
-    for (int d = 0; d < h->nd; ++d) {
-        uint32_t* pl = h->planes[h->cur] + (size_t)d * g.plane_stride + (size_t)first_row * g.pitch;
+    const int np = halo_planes(h, what);
+    for (int d = 0; d < np; ++d) {
+        uint32_t* base;
+        if (what == LGCA_B200_HALO_STATE) base = h->planes[h->cur] + (size_t)d * g.plane_stride;
+        else base = d == 0 ? h->ns : (d == 1 ? h->sl : h->ch);
+        uint32_t* pl = base + (size_t)first_row * g.pitch;
         uint8_t*  pk = (uint8_t*)packed + (size_t)d * g.halo * row_bytes;
         if (to_packed) LGCA_CUDA_CHECK(cudaMemcpyAsync(pk, pl, g.halo * row_bytes, cudaMemcpyDeviceToDevice, h->s_compute));
         else LGCA_CUDA_CHECK(cudaMemcpyAsync(pl, pk, g.halo * row_bytes, cudaMemcpyDeviceToDevice, h->s_compute));
@@ -573,31 +606,47 @@ static int halo_copy(lgca_b200_lattice* h, void* packed, uint32_t first_row, boo
     return 0;
 }
 
-int lgca_b200_halo_export(lgca_b200_lattice* h, void* dev_top_rows, void* dev_bottom_rows)
+int lgca_b200_halo_export(lgca_b200_lattice* h, int what, void* dev_top_rows, void* dev_bottom_rows)
 {
     if (!h || !dev_top_rows || !dev_bottom_rows) return set_error(LGCA_B200_EINVAL, "null argument");
     if (!h->g.halo) return set_error(LGCA_B200_ESTATE, "handle owns the whole lattice: no halo");
+    if (what != LGCA_B200_HALO_STATE && what != LGCA_B200_HALO_MASKS) return set_error(LGCA_B200_EINVAL, "bad halo kind");
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     const Geom& g = h->g;
-    // "top" = the strip's highest own rows (go to the upper neighbour's lower halo)
-    int rc = halo_copy(h, dev_top_rows, g.rows - 2 * g.halo, true);
-    if (!rc) rc = halo_copy(h, dev_bottom_rows, g.halo, true);
-    if (rc) return rc;
-    LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
-    return 0;
+    // "top" = the strip's highest own rows (they become the upper neighbour's lower halo)
+    int rc = halo_copy(h, what, dev_top_rows, g.rows - 2 * g.halo, true);
+    if (!rc) rc = halo_copy(h, what, dev_bottom_rows, g.halo, true);
+    return rc;
 }
 
-int lgca_b200_halo_import(lgca_b200_lattice* h, const void* dev_from_upper, const void* dev_from_lower)
+int lgca_b200_halo_import(lgca_b200_lattice* h, int what, const void* dev_from_upper, const void* dev_from_lower)
 {
     if (!h || !dev_from_upper || !dev_from_lower) return set_error(LGCA_B200_EINVAL, "null argument");
     if (!h->g.halo) return set_error(LGCA_B200_ESTATE, "handle owns the whole lattice: no halo");
+    if (what != LGCA_B200_HALO_STATE && what != LGCA_B200_HALO_MASKS) return set_error(LGCA_B200_EINVAL, "bad halo kind");
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     const Geom& g = h->g;
-    // rows from the upper neighbour (its bottom rows) fill the halo above the strip, and vice versa
-    int rc = halo_copy(h, const_cast<void*>(dev_from_upper), g.rows - g.halo, false);
-    if (!rc) rc = halo_copy(h, const_cast<void*>(dev_from_lower), 0, false);
-    if (rc) return rc;
-    LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
+    // the upper neighbour's bottom rows fill the halo above the strip, and vice versa
+    int rc = halo_copy(h, what, const_cast<void*>(dev_from_upper), g.rows - g.halo, false);
+    if (!rc) rc = halo_copy(h, what, const_cast<void*>(dev_from_lower), 0, false);
+    return rc;
+}
+
+// Wall-kind flags select the kernel variant; with row strips every rank must use the union of all
+// strips' flags (a strip without walls of its own may import wall cells in its halo rows).
+int lgca_b200_get_wall_flags(lgca_b200_lattice* h, uint32_t* has_no_slip, uint32_t* has_slip)
+{
+    if (!h || !has_no_slip || !has_slip) return set_error(LGCA_B200_EINVAL, "null argument");
+    *has_no_slip = (uint32_t)h->has_ns;
+    *has_slip = (uint32_t)h->has_sl;
+    return 0;
+}
+
+int lgca_b200_set_wall_flags(lgca_b200_lattice* h, uint32_t has_no_slip, uint32_t has_slip)
+{
+    if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
+    h->has_ns = has_no_slip != 0;
+    h->has_sl = has_slip != 0;
     return 0;
 }
 

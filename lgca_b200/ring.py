@@ -1,0 +1,99 @@
+"""Row-strip domain decomposition over the GPUs of one box: one process (rank) per GPU, one strip per rank.
+
+The reference has no decomposition at all (one shared-memory lattice); its torus is always
+periodic (src/omp_lattice.cpp:150-176), so the strips form a periodic ring in y: rank r's upper neighbour is
+(r+1) % world, its lower neighbour (r-1) % world.  After every block of at most `halo` fused steps each rank
+sends its top rows up and its bottom rows down and receives the matching ghost rows.  The transfer itself is
+torch.distributed point-to-point (NCCL over NVLink on GPUs, gloo in the CPU tests); pack/unpack of the rows is
+done by the engine on its own stream and everything is stream-ordered (no host synchronisation per block).
+
+This module is host-side plumbing only -- it never touches lattice data itself.
+"""
+import contextlib
+
+
+def partition_rows(dim_y, world, multiple=2):
+    """Split dim_y rows into `world` contiguous strips whose heights are multiples of `multiple`
+    (2 keeps the hexagonal row parity local == global; 2*cg_radius keeps coarse cells strip-local).
+    Returns [(y_begin, y_rows)] with the remainder spread over the first strips."""
+    if dim_y % multiple:
+        raise ValueError("dim_y must be a multiple of %d" % multiple)
+    units = dim_y // multiple
+    if units < world:
+        raise ValueError("lattice too small for %d strips" % world)
+    base, extra = divmod(units, world)
+    out, y = [], 0
+    for r in range(world):
+        rows = (base + (1 if r < extra else 0)) * multiple
+        out.append((y, rows))
+        y += rows
+    return out
+
+
+def ring_neighbours(rank, world):
+    """(lower, upper) ranks of the periodic ring."""
+    return (rank - 1) % world, (rank + 1) % world
+
+
+class Ring:
+    """Halo exchange driver for one strip.
+
+    `engine` needs: halo_rows(), halo_bytes(what), halo_export(what, top_ptr, bottom_ptr),
+    halo_import(what, from_upper_ptr, from_lower_ptr), step(n), compute_stream() (CUDA engines only).
+    """
+
+    STATE, MASKS = 0, 1
+
+    def __init__(self, engine, rank, world, device=None, group=None):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.e, self.rank, self.world, self.group = engine, rank, world, group
+        self.lower, self.upper = ring_neighbours(rank, world)
+        self.halo = engine.halo_rows()
+        self.device = device if device is not None else torch.device("cpu")
+        self._bufs = {}
+        self._stream = None
+        if self.device.type == "cuda":
+            # NCCL work is ordered against the engine's own compute stream
+            self._stream = torch.cuda.ExternalStream(engine.compute_stream(), device=self.device)
+        self.exchanges = 0
+
+    def _buffers(self, what):
+        if what not in self._bufs:
+            n = self.e.halo_bytes(what)
+            mk = lambda: self.torch.empty(n, dtype=self.torch.uint8, device=self.device)
+            self._bufs[what] = dict(top=mk(), bottom=mk(), from_upper=mk(), from_lower=mk())
+        return self._bufs[what]
+
+    def _ctx(self):
+        return self.torch.cuda.stream(self._stream) if self._stream is not None else contextlib.nullcontext()
+
+    def exchange(self, what=0):
+        """Send own top rows up / bottom rows down, receive the ghost rows, install them."""
+        if self.world == 1 or self.halo == 0:
+            return
+        b, dist = self._buffers(what), self.dist
+        with self._ctx():
+            self.e.halo_export(what, b["top"].data_ptr(), b["bottom"].data_ptr())
+            # order matters when lower == upper (world == 2): the peer's first send (its top rows) must meet
+            # our first recv (from_lower), its second (bottom rows) our second (from_upper)
+            ops = [dist.P2POp(dist.isend, b["top"], self.upper, self.group),
+                   dist.P2POp(dist.isend, b["bottom"], self.lower, self.group),
+                   dist.P2POp(dist.irecv, b["from_lower"], self.lower, self.group),
+                   dist.P2POp(dist.irecv, b["from_upper"], self.upper, self.group)]
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+            self.e.halo_import(what, b["from_upper"].data_ptr(), b["from_lower"].data_ptr())
+        self.exchanges += 1
+
+    def step(self, n):
+        """n lattice updates; ghost rows are refreshed after every block of <= halo steps."""
+        if self.world == 1 or self.halo == 0:
+            self.e.step(n)
+            return
+        while n > 0:
+            k = min(self.halo, n)
+            self.e.step(k)
+            self.exchange(self.STATE)
+            n -= k

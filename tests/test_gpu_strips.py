@@ -1,0 +1,88 @@
+"""Row strips on the GPU (run with -m gpu): several strip handles on ONE device, ghost rows moved with the
+same Ring-style export/import calls the multi-GPU bench uses (here by plain device pointers inside one
+process).  The union of the strips must equal the oracle's single-lattice run bit-exactly
+(decomposition invariance), including walls crossing strip borders and the odd/even hex rows."""
+import numpy as np
+import pytest
+
+from cpu_checkers import Oracle, OracleRng
+
+pytestmark = pytest.mark.gpu
+
+
+class LocalRing:
+    """All strips in one process: exports of every strip first, then imports from the ring neighbours."""
+
+    def __init__(self, engines):
+        import torch
+        self.t, self.e = torch, engines
+        self.n = len(engines)
+        self.buf = {}
+
+    def _b(self, what):
+        if what not in self.buf:
+            mk = lambda e: self.t.empty(e.halo_bytes(what), dtype=self.t.uint8, device="cuda")
+            self.buf[what] = [(mk(e), mk(e)) for e in self.e]
+        return self.buf[what]
+
+    def exchange(self, what=0):
+        b = self._b(what)
+        for e, (top, bottom) in zip(self.e, b):
+            e.halo_export(what, top.data_ptr(), bottom.data_ptr())
+        for e in self.e:
+            e.sync()
+        for r, e in enumerate(self.e):
+            upper, lower = (r + 1) % self.n, (r - 1) % self.n
+            # from the upper neighbour: its bottom rows; from the lower neighbour: its top rows
+            e.halo_import(what, b[upper][1].data_ptr(), b[lower][0].data_ptr())
+        for e in self.e:
+            e.sync()
+
+
+@pytest.mark.parametrize("model,dims,bc,nstrips,k", [
+    ("FHP_III", (256, 96), "karman", 2, 2),
+    ("FHP_III", (1000, 120), "periodic", 3, 4),
+    ("FHP_II", (512, 128), "reflecting_back", 4, 3),
+    ("FHP_I", (300, 64), "reflecting_forward", 2, 1),
+    ("HPP", (640, 90), "reflecting_forward", 3, 4),
+])
+def test_strips_equal_single_lattice(model, dims, bc, nstrips, k):
+    import lgca_b200
+    from lgca_b200.ring import partition_rows
+    o = Oracle(model, dims=dims, cg=1, rng=OracleRng(5))
+    o.apply_bc(bc)
+    o.init("random")
+    parts = partition_rows(dims[1], nstrips, 2)
+    engines = []
+    for y0, rows in parts:
+        e = lgca_b200.Engine(model, dims[0], dims[1], k_fuse=k, y_begin=y0, y_rows=rows)
+        sl = slice(y0 * dims[0], (y0 + rows) * dims[0])
+        e.upload(o.state[sl], o.cell_type[sl], o.rnd)
+        engines.append(e)
+    # every strip runs with the union of the wall kinds; ghost rows get the neighbours' masks once
+    flags = [e.wall_flags() for e in engines]
+    for e in engines:
+        e.set_wall_flags(any(f[0] for f in flags), any(f[1] for f in flags))
+    ring = LocalRing(engines)
+    ring.exchange(1)
+    ring.exchange(0)
+    halo = engines[0].halo_rows()
+    assert halo >= k and halo % 2 == 0
+    done = 0
+    for n in (1, k, 2 * k + 1, 7):
+        left = n
+        while left > 0:
+            b = min(left, halo)
+            for e in engines:
+                e.step(b)
+            ring.exchange(0)
+            left -= b
+        o.step(n)
+        done += n
+        got = np.concatenate([e.download() for e in engines])
+        assert np.array_equal(got, o.state), "after %d steps" % done
+    assert sum(e.count_particles() for e in engines) == o.n_particles()
+    with pytest.raises(lgca_b200.LgcaError):
+        engines[0].step(halo + 1)  # a strip may not run past its ghost rows
+    for e in engines:
+        e.close()
