@@ -230,6 +230,7 @@ int lgca_b200_upload(lgca_b200_lattice* h, const uint8_t* state, const int32_t* 
         LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
         h->has_ns = flags[0] != 0;
         h->has_sl = flags[1] != 0;
+        memset(h->plan_valid, 0, sizeof(h->plan_valid));
         h->have_types = 1;
     }
     if (rnd_bits) {
@@ -504,6 +505,7 @@ int lgca_b200_apply_bc_device(lgca_b200_lattice* h, const char* bc)
     LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
     h->has_ns = (kind >= 1 && kind <= 3);
     h->has_sl = (kind == 4);
+    memset(h->plan_valid, 0, sizeof(h->plan_valid));
     h->have_types = 1;
     return 0;
 }
@@ -647,6 +649,7 @@ int lgca_b200_set_wall_flags(lgca_b200_lattice* h, uint32_t has_no_slip, uint32_
     if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
     h->has_ns = has_no_slip != 0;
     h->has_sl = has_slip != 0;
+    memset(h->plan_valid, 0, sizeof(h->plan_valid));
     return 0;
 }
 

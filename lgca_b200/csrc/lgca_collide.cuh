@@ -13,9 +13,10 @@
 //
 // The networks are NOT transcriptions of the reference's formulas: they are re-derived from the
 // collision table to minimise 3-input logic ops (the integer pipe is the co-limiter of this kernel):
-// a bit-sliced population count of the six movers classifies each site as "exactly 1/2/3 movers",
-// head-on pairs and symmetric triples are detected from that, and the rest-particle rules of FHP-II
-// collapse to "flip a trio of adjacent directions and the rest bit" around a centre direction.
+// the movers of the two triangles (even / odd directions) are counted with one full adder each, which
+// classifies every site (one mover, head-on candidate, 120-degree pair, alternating triple) in a few ops;
+// the rest-particle rules of FHP-II collapse to "flip a trio of adjacent directions and the rest bit".
+// About 40 LOP3 per 32 sites for FHP-II/III (the reference's formulas lifted verbatim need 76).
 #pragma once
 #include <stdint.h>
 
@@ -79,60 +80,59 @@ LGCA_HD void collide_hpp(uint32_t (&n)[7])
 //   p = chirality word (frozen per-site random bit, src/omp_lattice.cpp:84,198):
 //   head-on pair (i,i+3), all other movers empty  -> rotates to (i+1,i+4) if p==0, (i-1,i+2) if p==1
 //   symmetric triple (0,2,4)<->(1,3,5)
-//   FHP-II: rest + single mover i            -> movers i-1,i+1 (rest consumed)
-//           movers i-1,i+1 only, no rest     -> mover i + rest
-// In change-mask form (out = in ^ ch), the pair (i, i+3) shares its head-on/triple mask T and the two
-// rest rules both flip the trio {c-1,c,c+1} plus the rest bit around a centre direction c.
+//   FHP-II: rest + single mover c             -> movers c-1,c+1 (rest consumed)
+//           movers c-1,c+1 only, no rest      -> mover c + rest
+//
+// Network (change-mask form, out = in ^ ch).  The six movers are counted per TRIANGLE -- even
+// directions (0,2,4) and odd directions (1,3,5) -- with one full adder each:
+//     s_e,c_e = XOR3/MAJ(n0,n2,n4)     s_o,c_o = XOR3/MAJ(n1,n3,n5)
+// which classifies every site with a handful of 3-input ops:
+//     exactly one mover            one = (s_e^s_o) & ~(c_e|c_o)
+//     one even + one odd mover     g1  = s_e & s_o & ~(c_e|c_o)      (adjacent or head-on pair)
+//     two movers of one triangle   d2  = ~s_e & ~s_o & (c_e^c_o)     (always 120 degrees apart)
+//     alternating triple           tri = (s_e^s_o) & (c_e^c_o) & ~(s_e^c_e)
+// Head-on pairs are g1 & n_j & n_{j+3}.  Both rest rules flip the trio {c-1,c,c+1} and the rest bit
+// around a centre c, and fire exactly when  E = r ? one : d2 ; direction i then flips iff
+// E & (n_i | (r ? n_{i-1}|n_{i+1} : n_{i-1}&n_{i+1})).
 // ---------------------------------------------------------------------------------------------
 template <bool WITH_REST>
 LGCA_HD void collide_fhp(uint32_t (&n)[7], uint32_t p)
 {
-    // bit-sliced count of the six movers: cnt = s1 + s2 + 2*(c1 + c2)
-    const uint32_t s1 = lop3<LUT_XOR3>(n[0], n[1], n[2]);
-    const uint32_t c1 = lop3<LUT_MAJ>(n[0], n[1], n[2]);
-    const uint32_t s2 = lop3<LUT_XOR3>(n[3], n[4], n[5]);
-    const uint32_t c2 = lop3<LUT_MAJ>(n[3], n[4], n[5]);
-    const uint32_t cor = c1 | c2, cxr = c1 ^ c2;
-    // exactly two movers: (s1 & s2 & no carries) | (no ones & exactly one carry)
-    const uint32_t two_a = lop3<TA & TB & ~TC>(s1, s2, cor);
-    const uint32_t two_b = lop3<TA | (~TB & ~TC & 0xFF)>(two_a, s1, s2); // two_a | (~s1 & ~s2)
-    const uint32_t g2    = lop3<TA & (TB | TC)>(two_b, two_a, cxr);      // two_a | (~s1 & ~s2 & (c1^c2))
-    // head-on pairs
-    const uint32_t h1 = lop3<LUT_AND3>(n[1], n[4], g2); // dirs 1,4  (reference "db1")
-    const uint32_t h2 = lop3<LUT_AND3>(n[2], n[5], g2); // dirs 2,5  ("db2")
-    const uint32_t h3 = lop3<LUT_AND3>(n[0], n[3], g2); // dirs 3,0  ("db3")
-    // symmetric triples: the six movers alternate
-    const uint32_t u1  = lop3<(TA ^ TB) & (TB ^ TC)>(n[0], n[1], n[2]);
-    const uint32_t u2  = lop3<(TA ^ TB) & (TB ^ TC)>(n[2], n[3], n[4]);
-    const uint32_t u3  = lop3<TA & (TB ^ TC)>(u1, n[4], n[5]);
-    const uint32_t tri = u2 & u3;
+    const uint32_t se = lop3<LUT_XOR3>(n[0], n[2], n[4]);
+    const uint32_t ce = lop3<LUT_MAJ>(n[0], n[2], n[4]);
+    const uint32_t so = lop3<LUT_XOR3>(n[1], n[3], n[5]);
+    const uint32_t co = lop3<LUT_MAJ>(n[1], n[3], n[5]);
+    const uint32_t cor = ce | co, cxr = ce ^ co;
+    const uint32_t g1  = lop3<TA & TB & ~TC>(se, so, cor);
+    // head-on pairs (reference: db1 = dirs 1,4; db2 = dirs 2,5; db3 = dirs 3,0)
+    const uint32_t h1 = lop3<LUT_AND3>(n[1], n[4], g1);
+    const uint32_t h2 = lop3<LUT_AND3>(n[2], n[5], g1);
+    const uint32_t h3 = lop3<LUT_AND3>(n[0], n[3], g1);
+    // symmetric triple
+    const uint32_t sx  = se ^ so;
+    const uint32_t tri = lop3<TA & TB & ~TC>(sx, cxr, se ^ ce);
     // per-pair change masks: T14 = tri | h1 | (p ? h2 : h3), ...
-    uint32_t t14 = lop3<LUT_OR3>(tri, h1, lop3<LUT_MUX>(p, h2, h3));
-    uint32_t t25 = lop3<LUT_OR3>(tri, h2, lop3<LUT_MUX>(p, h3, h1));
-    uint32_t t30 = lop3<LUT_OR3>(tri, h3, lop3<LUT_MUX>(p, h1, h2));
+    const uint32_t t14 = lop3<LUT_OR3>(tri, h1, lop3<LUT_MUX>(p, h2, h3));
+    const uint32_t t25 = lop3<LUT_OR3>(tri, h2, lop3<LUT_MUX>(p, h3, h1));
+    const uint32_t t30 = lop3<LUT_OR3>(tri, h3, lop3<LUT_MUX>(p, h1, h2));
 
     if (WITH_REST) {
         const uint32_t r   = n[6];
-        const uint32_t one = lop3<(TA ^ TB) & ~TC>(s1, s2, cor); // exactly one mover
-        const uint32_t H   = r & one;                            // rest + single mover
-        const uint32_t G   = g2 & ~r;                            // two movers, no rest
-        uint32_t cen[6];
-#pragma unroll
-        for (int i = 0; i < 6; ++i) {
-            const uint32_t t = lop3<LUT_AND3>(G, n[(i + 5) % 6], n[(i + 1) % 6]);
-            cen[i] = lop3<(TA & TB) | TC>(H, n[i], t);
-        }
-        const uint32_t chr = lop3<LUT_OR3>(cen[0], cen[1], cen[2]) | lop3<LUT_OR3>(cen[3], cen[4], cen[5]);
+        const uint32_t one = lop3<TA & ~TB>(sx, cor, 0u);          // exactly one mover
+        const uint32_t d2  = lop3<~TA & ~TB & TC & 0xFF>(se, so, cxr); // two movers 120 degrees apart
+        const uint32_t E   = lop3<LUT_MUX>(r, one, d2);           // a rest rule fires (== change of the rest bit)
         uint32_t o[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            const uint32_t R = lop3<LUT_OR3>(cen[(i + 5) % 6], cen[i], cen[(i + 1) % 6]);
+            // y = r ? (n_{i-1} | n_{i+1}) : (n_{i-1} & n_{i+1})
+            const uint32_t y = lop3<(TA & (TB | TC)) | (~TA & TB & TC & 0xFF)>(r, n[(i + 5) % 6], n[(i + 1) % 6]);
+            const uint32_t R = lop3<TA & (TB | TC)>(E, n[i], y);
             const uint32_t T = (i == 1 || i == 4) ? t14 : ((i == 2 || i == 5) ? t25 : t30);
             o[i] = lop3<LUT_XOR_OR>(n[i], T, R);
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) n[i] = o[i];
-        n[6] = r ^ chr;
+        n[6] = r ^ E;
     } else {
         n[1] ^= t14; n[4] ^= t14;
         n[2] ^= t25; n[5] ^= t25;
@@ -164,20 +164,16 @@ template <int MODEL> LGCA_HD constexpr int mir_y_dir(int d) // mirror at the y a
     return rule_of(MODEL) == MODEL_HPP ? ((d & 1) ? d : (d ^ 2)) : (d == 6 ? 6 : (9 - d) % 6);
 }
 
-// Collision + wall handling of one word of sites (SURVEY A.4 / src/omp_lattice.cpp:193-231):
-//   fluid      -> collide
+// Wall handling of one word of sites (SURVEY A.4 / src/omp_lattice.cpp:193-231), applied on top of the
+// collided values n[] given the streamed-in (pre-collision) values in[]:
 //   no-slip    -> out[d] = in[INV d]
 //   slip       -> MIR_Y on E/W edge columns, else MIR_X on N/S edge rows, else pass-through
 // `ns`/`sl` are the solid masks, `ew` the mask of sites on the E/W domain edge, `ns_row` all-ones when
 // the row is the northern or southern domain edge.
 template <int MODEL, bool HAS_NS, bool HAS_SL>
-LGCA_HD void collide_and_walls(uint32_t (&n)[7], uint32_t p, uint32_t ns, uint32_t sl, uint32_t ew, uint32_t ns_row)
+LGCA_HD void apply_walls(uint32_t (&n)[7], const uint32_t (&in)[7], uint32_t ns, uint32_t sl, uint32_t ew, uint32_t ns_row)
 {
     constexpr int ND = num_dir_of(MODEL);
-    uint32_t in[7];
-#pragma unroll
-    for (int d = 0; d < ND; ++d) in[d] = n[d];
-    collide<MODEL>(n, p);
     if (HAS_NS) {
 #pragma unroll
         for (int d = 0; d < ND; ++d) n[d] = lop3<LUT_MUX>(ns, in[inv_dir<MODEL>(d)], n[d]);
@@ -190,6 +186,18 @@ LGCA_HD void collide_and_walls(uint32_t (&n)[7], uint32_t p, uint32_t ns, uint32
             n[d]       = lop3<LUT_MUX>(sl, s, n[d]);
         }
     }
+}
+
+// Collision + walls: fluid sites collide, solid sites reflect.
+template <int MODEL, bool HAS_NS, bool HAS_SL>
+LGCA_HD void collide_and_walls(uint32_t (&n)[7], uint32_t p, uint32_t ns, uint32_t sl, uint32_t ew, uint32_t ns_row)
+{
+    constexpr int ND = num_dir_of(MODEL);
+    uint32_t in[7];
+#pragma unroll
+    for (int d = 0; d < 7; ++d) in[d] = d < ND ? n[d] : 0u;
+    collide<MODEL>(n, p);
+    apply_walls<MODEL, HAS_NS, HAS_SL>(n, in, ns, sl, ew, ns_row);
 }
 
 } // namespace lgca_b200

@@ -37,18 +37,31 @@ __device__ __forceinline__ uint32_t down1(uint32_t w) // site x <- site x+1
     return __funnelshift_r(w, __shfl_down_sync(0xFFFFFFFFu, w, 1), 1);
 }
 
+// Kernel arguments: per-plane base pointers live in the constant parameter bank, so an address is one
+// IMAD.WIDE (32-bit word offset * 4 + constant base) on the FMA pipe instead of integer-pipe LEA pairs.
+struct WaveArgs {
+    const uint32_t* in[7];
+    uint32_t*       out[7];
+    const uint32_t* ns;
+    const uint32_t* sl;
+    const uint32_t* ch;
+    const uint32_t* xedge;
+};
+
 // Per-lane view of the periodic row: where this lane's 32 sites come from.
 template <bool IRREG>
 struct LaneSrc {
-    int  wa, wb, sh, n1;
-    bool regular;
-    __device__ __forceinline__ uint32_t load(const uint32_t* __restrict__ row) const
+    uint32_t wa, wb;
+    int      sh, n1;
+    bool     regular;
+    // row_off = word offset of the row start inside a plane
+    __device__ __forceinline__ uint32_t load(const uint32_t* __restrict__ plane, uint32_t row_off) const
     {
-        uint32_t v = __ldg(row + wa);
+        uint32_t v = __ldg(plane + (row_off + wa));
         if (IRREG) {
             if (!regular) { // lanes at the row end of a width that is not a multiple of 32
-                v = __funnelshift_r(v, __ldg(row + wb), sh);
-                if (n1 < 32) v = (v & low_mask(n1)) | (__ldg(row) << n1);
+                v = __funnelshift_r(v, __ldg(plane + (row_off + wb)), sh);
+                if (n1 < 32) v = (v & low_mask(n1)) | (__ldg(plane + row_off) << n1);
             }
         }
         return v;
@@ -61,43 +74,39 @@ struct WaveState {
     // delay lines of the level transition s-1 -> s (index s-1): planes of the previous row (C*) and
     // planes 1,2 of the row before that (D*)
     uint32_t C0[K], C1[K], C2[K], C3[K], C6[K], D1[K], D2[K];
-    uint32_t nxt[7];          // prefetched level-0 row
-    uint32_t m_p, m_ns, m_sl; // prefetched masks of the row that level 1 produces next
-    int      r0m;             // stored index of the level-0 row that arrived last
+    uint32_t nxt[7];                 // prefetched level-0 row
+    uint32_t Mp[K], Mns[K], Msl[K];  // mask words of the rows the levels produce next: index s-1 <-> row r0 - s
+    uint32_t r0m;                    // stored index of the level-0 row that arrived last
 };
 
 // One iteration: level-0 row r0 arrives, every level s produces its row r0 - s, and the level-K row
 // r0 - K is stored.  PAR = parity of the iteration index (compile time); WARM = pipeline still filling
 // (levels whose inputs are not there yet are skipped, nothing is stored before iteration 2K).
 template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG, int PAR, bool WARM>
-__device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>& src, int jc, int ya,
-                                         const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                         const uint32_t* __restrict__ ns_p, const uint32_t* __restrict__ sl_p,
-                                         const uint32_t* __restrict__ ch_p, const Geom& g, uint32_t ew, bool store_lane,
-                                         uint32_t vmask, int wi)
+__device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>& src, int jc, uint32_t out_off,
+                                         const WaveArgs& A, const Geom& g, uint32_t ew, bool store_lane, uint32_t vmask)
 {
     constexpr int  ND  = num_dir_of(MODEL);
     constexpr bool HPP = rule_of(MODEL) == MODEL_HPP;
-    const int rows = (int)g.rows;
+    const uint32_t rows = g.rows;
 
     uint32_t a[7];
 #pragma unroll
     for (int d = 0; d < ND; ++d) a[d] = st.nxt[d];
-    // masks for level 1 (row r0 - 1) were prefetched during the previous iteration
-    const uint32_t p1 = st.m_p, ns1 = st.m_ns, sl1 = st.m_sl;
 
     if (++st.r0m >= rows) st.r0m -= rows; // stored index of the arriving row r0
+    // prefetch the next level-0 row (r0 + 1) and the mask words of row r0 (level 1 needs them next time).
+    // Past the end of the chunk this reads a valid but unneeded row.
+    uint32_t pm = 0u, pns = 0u, psl = 0u;
     {
-        // prefetch the next level-0 row (r0 + 1) and the masks of row r0 (level 1 needs them next
-        // time).  Past the end of the chunk this reads a valid but unneeded row.
-        const int    rn = (st.r0m + 1 >= rows) ? st.r0m + 1 - rows : st.r0m + 1;
-        const size_t r  = (size_t)rn * g.pitch;
+        const uint32_t rn = (st.r0m + 1 >= rows) ? st.r0m + 1 - rows : st.r0m + 1;
+        const uint32_t ro = rn * g.pitch;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) st.nxt[d] = src.load(in + (size_t)d * g.plane_stride + r);
-        const size_t rm = (size_t)st.r0m * g.pitch;
-        if (!HPP) st.m_p = src.load(ch_p + rm);
-        if (HAS_NS) st.m_ns = src.load(ns_p + rm);
-        if (HAS_SL) st.m_sl = src.load(sl_p + rm);
+        for (int d = 0; d < ND; ++d) st.nxt[d] = src.load(A.in[d], ro);
+        const uint32_t rm = st.r0m * g.pitch;
+        if (!HPP) pm = src.load(A.ch, rm);
+        if (HAS_NS) pns = src.load(A.ns, rm);
+        if (HAS_SL) psl = src.load(A.sl, rm);
     }
 #pragma unroll
     for (int s = 1; s <= K; ++s) {
@@ -129,21 +138,27 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>&
                     n[5] = a[5];
                 }
             }
-            int ym = st.r0m - s; // stored index of row r0 - s (rows >= 2K)
-            if (ym < 0) ym += rows;
-            uint32_t p = 0u, ns = 0u, sl = 0u;
-            if (s == 1) {
-                p = p1; ns = ns1; sl = sl1;
+            const uint32_t p  = HPP ? 0u : st.Mp[s - 1];
+            const uint32_t ns = HAS_NS ? st.Mns[s - 1] : 0u;
+            const uint32_t sl = HAS_SL ? st.Msl[s - 1] : 0u;
+            if (HAS_NS || HAS_SL) {
+                // walls are rare: skip their logic for warps whose 1024 sites are all fluid
+                uint32_t in[7];
+#pragma unroll
+                for (int d = 0; d < 7; ++d) in[d] = n[d];
+                collide<MODEL>(n, p);
+                if (__any_sync(0xFFFFFFFFu, (ns | sl) != 0u)) {
+                    uint32_t ns_row = 0u;
+                    if (HAS_SL) {
+                        uint32_t ym = st.r0m + rows - (uint32_t)s; // stored index of row r0 - s
+                        if (ym >= rows) ym -= rows;
+                        ns_row = (ym == g.row_south || ym == g.row_north) ? 0xFFFFFFFFu : 0u;
+                    }
+                    apply_walls<MODEL, HAS_NS, HAS_SL>(n, in, ns, sl, ew, ns_row);
+                }
             } else {
-                // deeper levels re-read their mask words (this lane loaded them s-1 iterations ago: L1 hits)
-                const size_t rm = (size_t)ym * g.pitch;
-                if (!HPP) p = src.load(ch_p + rm);
-                if (HAS_NS) ns = src.load(ns_p + rm);
-                if (HAS_SL) sl = src.load(sl_p + rm);
+                collide<MODEL>(n, p);
             }
-            const uint32_t ns_row =
-                (HAS_SL && ((uint32_t)ym == g.row_south || (uint32_t)ym == g.row_north)) ? 0xFFFFFFFFu : 0u;
-            collide_and_walls<MODEL, HAS_NS, HAS_SL>(n, p, ns, sl, ew, ns_row);
         }
         // rotate the delay line of this level transition
         st.D1[s - 1] = st.C1[s - 1];
@@ -160,25 +175,29 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>&
 #pragma unroll
         for (int d = 0; d < ND; ++d) a[d] = n[d];
     }
-    if ((!WARM || jc >= 2 * K) && store_lane) {
-        const size_t ro = (size_t)(ya - 2 * K + jc) * g.pitch + wi;
+    // masks travel down the levels with the rows they belong to
 #pragma unroll
-        for (int d = 0; d < ND; ++d) out[(size_t)d * g.plane_stride + ro] = IRREG ? (a[d] & vmask) : a[d];
+    for (int s = K - 1; s >= 1; --s) {
+        if (!HPP) st.Mp[s] = st.Mp[s - 1];
+        if (HAS_NS) st.Mns[s] = st.Mns[s - 1];
+        if (HAS_SL) st.Msl[s] = st.Msl[s - 1];
+    }
+    st.Mp[0] = pm; st.Mns[0] = pns; st.Msl[0] = psl;
+
+    if ((!WARM || jc >= 2 * K) && store_lane) {
+#pragma unroll
+        for (int d = 0; d < ND; ++d) A.out[d][out_off] = IRREG ? (a[d] & vmask) : a[d];
     }
 }
 
 template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
-__global__ void __launch_bounds__(128) step_wave_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out,
-                                                        const uint32_t* __restrict__ ns_p,
-                                                        const uint32_t* __restrict__ sl_p,
-                                                        const uint32_t* __restrict__ ch_p,
-                                                        const uint32_t* __restrict__ xedge, const Geom g,
-                                                        const WavePlan wp)
+__global__ void __launch_bounds__(32) step_wave_kernel(const WaveArgs A, const Geom g, const WavePlan wp)
 {
     constexpr int ND = num_dir_of(MODEL);
-    const int lane = threadIdx.x & 31;
-    const int tile = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (tile >= wp.tiles) return;
+    const int lane = threadIdx.x;
+    // one warp per block: the tile index (and with it every loop bound) is provably warp-uniform, so the
+    // shuffles in the row loop compile to plain SHFL without convergence bookkeeping
+    const int tile = blockIdx.x;
     const int band  = tile % wp.bands;
     const int chunk = tile / wp.bands;
     const int wi    = band * WAVE_VALID - 1 + lane;          // word column of this lane (may be -1 / >= nw)
@@ -192,44 +211,51 @@ __global__ void __launch_bounds__(128) step_wave_kernel(const uint32_t* __restri
     //   * otherwise lanes whose 32 sites touch the row end assemble them from up to three words
     //     (two around bit position p, plus word 0 after the wrap) with precomputed indices/shifts.
     LaneSrc<IRREG> src;
-    src.wa = wi; src.wb = 0; src.sh = 0; src.n1 = 32; src.regular = true;
-    if (!IRREG) {
-        if (src.wa < 0) src.wa += (int)g.nw;
-        else if (src.wa >= (int)g.nw) src.wa %= (int)g.nw;
-    } else {
-        src.regular = (wi >= 0) && (wi < (int)g.nw - 1);
-        if (!src.regular) {
-            long long p = ((long long)wi * 32) % (long long)g.dim_x;
-            if (p < 0) p += g.dim_x;
-            src.wa = (int)(p >> 5);
-            src.sh = (int)(p & 31);
-            src.wb = min(src.wa + 1, (int)g.nw - 1);
-            src.n1 = (int)min((long long)32, (long long)g.dim_x - p); // sites before the row end
+    src.wb = 0; src.sh = 0; src.n1 = 32; src.regular = true;
+    {
+        int wa = wi;
+        if (!IRREG) {
+            if (wa < 0) wa += (int)g.nw;
+            else if (wa >= (int)g.nw) wa %= (int)g.nw;
+        } else {
+            src.regular = (wi >= 0) && (wi < (int)g.nw - 1);
+            if (!src.regular) {
+                long long p = ((long long)wi * 32) % (long long)g.dim_x;
+                if (p < 0) p += g.dim_x;
+                wa      = (int)(p >> 5);
+                src.sh  = (int)(p & 31);
+                src.wb  = (uint32_t)min(wa + 1, (int)g.nw - 1);
+                src.n1  = (int)min((long long)32, (long long)g.dim_x - p); // sites before the row end
+            }
         }
+        src.wa = (uint32_t)wa;
     }
     const bool     store_lane = (lane >= 1) && (lane <= WAVE_VALID) && (wi < (int)g.nw);
     const uint32_t vmask      = store_lane ? valid_mask(g, wi) : 0u;
-    const uint32_t ew         = HAS_SL ? src.load(xedge) : 0u;
+    const uint32_t ew         = HAS_SL ? src.load(A.xedge, 0u) : 0u;
 
     WaveState<K> st;
 #pragma unroll
-    for (int s = 0; s < K; ++s) st.C0[s] = st.C1[s] = st.C2[s] = st.C3[s] = st.C6[s] = st.D1[s] = st.D2[s] = 0u;
-    st.m_p = st.m_ns = st.m_sl = 0u;
-    st.r0m = ya - K;
-    if (st.r0m < 0) st.r0m += rows;
+    for (int s = 0; s < K; ++s) {
+        st.C0[s] = st.C1[s] = st.C2[s] = st.C3[s] = st.C6[s] = st.D1[s] = st.D2[s] = 0u;
+        st.Mp[s] = st.Mns[s] = st.Msl[s] = 0u;
+    }
+    int r0 = ya - K;
+    if (r0 < 0) r0 += rows;
     {
-        const size_t r = (size_t)st.r0m * g.pitch;
+        const uint32_t ro = (uint32_t)r0 * g.pitch;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) st.nxt[d] = src.load(in + (size_t)d * g.plane_stride + r);
+        for (int d = 0; d < ND; ++d) st.nxt[d] = src.load(A.in[d], ro);
 #pragma unroll
         for (int d = ND; d < 7; ++d) st.nxt[d] = 0u;
     }
-    --st.r0m; // wave_row advances it to the arriving row first thing
+    st.r0m = (uint32_t)(r0 == 0 ? rows - 1 : r0 - 1); // wave_row advances it to the arriving row first thing
 
+    // word offset of the row stored by the current iteration (row ya - 2K + jc), advanced per row
+    uint32_t out_off = (uint32_t)ya * g.pitch + (uint32_t)max(wi, 0);
 #define LGCA_ROW(PAR, WARM, JC)                                                                                      \
-    wave_row<MODEL, K, HAS_NS, HAS_SL, IRREG, PAR, WARM>(st, src, JC, ya, in, out, ns_p, sl_p, ch_p, g, ew, store_lane, \
-                                                        vmask, wi)
-    // pipeline fill: iterations 0 .. 2K-1 (2K is even, so parities alternate from 0)
+    wave_row<MODEL, K, HAS_NS, HAS_SL, IRREG, PAR, WARM>(st, src, JC, out_off, A, g, ew, store_lane, vmask)
+    // pipeline fill: iterations 0 .. 2K-1 store nothing (2K is even, so parities alternate from 0)
 #pragma unroll 1
     for (int j = 0; j < 2 * K; j += 2) {
         LGCA_ROW(0, true, j);
@@ -240,7 +266,9 @@ __global__ void __launch_bounds__(128) step_wave_kernel(const uint32_t* __restri
 #pragma unroll 1
     for (; j + 1 < total; j += 2) {
         LGCA_ROW(0, false, j);
+        out_off += g.pitch;
         LGCA_ROW(1, false, j + 1);
+        out_off += g.pitch;
     }
     if (j < total) LGCA_ROW(0, false, j); // odd number of rows (HPP lattices with odd height)
 #undef LGCA_ROW
@@ -248,9 +276,9 @@ __global__ void __launch_bounds__(128) step_wave_kernel(const uint32_t* __restri
 
 // Chunk height: enough tiles to fill the machine, long enough to amortise the K-row pipeline fill.
 // Cost model per fused step: every tile runs (cr + k - 1) level-rows (the fill is trapezoidal); tiles run
-// in rounds of `resident` warps per SM; an SM with fewer than `saturate` warps is latency-bound and
-// modelled as proportionally slower.
-static WavePlan make_plan(const lgca_b200_lattice* h, int k)
+// in rounds of `resident` warps per SM (from the occupancy of the kernel variant); an SM holding fewer
+// warps than that hides less latency and is modelled as sub-linearly slower.
+static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
 {
     const Geom& g = h->g;
     WavePlan wp;
@@ -258,14 +286,14 @@ static WavePlan make_plan(const lgca_b200_lattice* h, int k)
     const int rows = (int)g.rows;
     const char* e_cr = getenv("LGCA_B200_CHUNK_ROWS");
     const char* e_res = getenv("LGCA_B200_RESIDENT_WARPS");
-    const double resident = e_res ? atof(e_res) : 16.0, saturate = 12.0;
+    const double resident = e_res ? atof(e_res) : (double)resident_warps;
     int    best_cr = (rows + 1) & ~1;
     double best = 1e300;
     for (int cr = 2 * k; cr <= rows + 1; cr += 2) {
         const int    chunks = (rows + cr - 1) / cr;
         const double w      = (double)chunks * wp.bands / 148.0; // warps per SM
         const double rounds = fmax(1.0, ceil(w / resident));
-        const double eff    = fmin(1.0, (w / rounds) / saturate);
+        const double eff    = pow(fmin(1.0, (w / rounds) / resident), 0.6);
         const double cost   = (double)(cr + k - 1) * rounds / eff;
         if (cost <= best) { best = cost; best_cr = cr; }
     }
@@ -289,28 +317,39 @@ bool wave_supported(const lgca_b200_lattice* h, int k)
     return true;
 }
 
-template <int MODEL, int K>
-static int launch_mk(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s)
+template <int MODEL, int K, bool NS, bool SL, bool IRREG>
+static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s)
 {
-    if (!h->plan_valid[K]) { h->plans[K] = make_plan(h, K); h->plan_valid[K] = 1; }
+    auto kernel = step_wave_kernel<MODEL, K, NS, SL, IRREG>;
+    if (!h->plan_valid[K]) {
+        int blocks = 0;
+        LGCA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, 32, 0));
+        h->plans[K] = make_plan(h, K, blocks > 0 ? blocks : 16);
+        h->plan_valid[K] = 1;
+    }
     const WavePlan wp = h->plans[K];
-    const int warps_per_block = 4;
-    dim3 block(32 * warps_per_block, 1, 1);
-    dim3 grid((wp.tiles + warps_per_block - 1) / warps_per_block, 1, 1);
-    const bool irreg = h->g.rem != 0;
-#define GO(NS, SL)                                                                                                \
-    do {                                                                                                          \
-        if (irreg) step_wave_kernel<MODEL, K, NS, SL, true><<<grid, block, 0, s>>>(in, out, h->ns, h->sl, h->ch,  \
-                                                                                    h->xedge, h->g, wp);          \
-        else step_wave_kernel<MODEL, K, NS, SL, false><<<grid, block, 0, s>>>(in, out, h->ns, h->sl, h->ch,       \
-                                                                               h->xedge, h->g, wp);               \
-    } while (0)
-    if (h->has_sl) { if (h->has_ns) GO(true, true); else GO(false, true); }
-    else           { if (h->has_ns) GO(true, false); else GO(false, false); }
-#undef GO
+    WaveArgs A;
+    for (int d = 0; d < 7; ++d) {
+        const size_t off = (size_t)(d < h->nd ? d : 0) * h->g.plane_stride;
+        A.in[d]  = in + off;
+        A.out[d] = out + off;
+    }
+    A.ns = h->ns; A.sl = h->sl; A.ch = h->ch; A.xedge = h->xedge;
+    kernel<<<dim3(wp.tiles, 1, 1), dim3(32, 1, 1), 0, s>>>(A, h->g, wp);
     h->launches++;
     LGCA_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+template <int MODEL, int K>
+static int launch_mk(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s)
+{
+    if ((uint64_t)h->g.rows * h->g.pitch > 0xFFFFFFFFull) return set_error(LGCA_B200_EINVAL, "plane too large for 32-bit word offsets");
+    const bool irreg = h->g.rem != 0;
+#define GO(NS, SL) (irreg ? launch_variant<MODEL, K, NS, SL, true>(h, in, out, s) : launch_variant<MODEL, K, NS, SL, false>(h, in, out, s))
+    if (h->has_sl) return h->has_ns ? GO(true, true) : GO(false, true);
+    return h->has_ns ? GO(true, false) : GO(false, false);
+#undef GO
 }
 
 template <int MODEL>

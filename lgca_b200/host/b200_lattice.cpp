@@ -1,0 +1,277 @@
+// B200_Lattice<Model> -- see b200_lattice.h.  Host C++ on top of the C-ABI; no lattice arithmetic here.
+#include "b200_lattice.h"
+
+#include <algorithm>
+#include <cstring>
+
+#include "../../include/lgca_b200.h"
+
+namespace lgca {
+
+namespace {
+void* pinned_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (lgca_b200_host_alloc(bytes, &p) != 0) {
+        printf("ERROR in B200_Lattice::allocate_memory(): %s\n", lgca_b200_last_error());
+        abort();
+    }
+    return p;
+}
+void pinned_free(void* p) { lgca_b200_host_free(p); }
+} // namespace
+
+template <Model model_>
+void B200_Lattice<model_>::fail(const char* where, int rc)
+{
+    printf("ERROR in B200_Lattice::%s(): %s (code %d)\n", where, lgca_b200_last_error(), rc);
+    abort();
+}
+
+template <Model model_>
+B200_Lattice<model_>::B200_Lattice(const string test_case, const Real Re, const Real Ma_s, const int cg, const B200Options& opt)
+    : Lattice<model_>(test_case, Re, Ma_s, cg), m_opt(opt)
+{
+    allocate_memory();
+    this->m_rnd_cpu.fill_random(); // right after allocation, before any initialiser: rand() stream order
+    create_device_lattice();
+}
+
+template <Model model_>
+B200_Lattice<model_>::B200_Lattice(const string test_case, unsigned int dim_x, unsigned int dim_y, const int cg, char bf_dir,
+                                   const B200Options& opt)
+    : Lattice<model_>(test_case, dim_x, dim_y, cg, bf_dir), m_opt(opt)
+{
+    allocate_memory();
+    this->m_rnd_cpu.fill_random();
+    create_device_lattice();
+}
+
+template <Model model_>
+B200_Lattice<model_>::~B200_Lattice()
+{
+    if (m_h) lgca_b200_destroy(m_h);
+    free_memory();
+}
+
+template <Model model_>
+void B200_Lattice<model_>::allocate_memory()
+{
+    const size_t n = this->m_num_cells, nc = std::max<size_t>(this->m_num_coarse_cells, 1);
+    this->m_cell_type_cpu = static_cast<CellType*>(pinned_alloc(n * sizeof(CellType)));
+    std::memset(this->m_cell_type_cpu, 0, n * sizeof(CellType));
+    if (m_opt.cell_fields) {
+        this->m_cell_density_cpu  = static_cast<Real*>(pinned_alloc(n * sizeof(Real)));
+        this->m_cell_momentum_cpu = static_cast<Real*>(pinned_alloc(2 * n * sizeof(Real)));
+        std::memset(this->m_cell_density_cpu, 0, n * sizeof(Real));
+        std::memset(this->m_cell_momentum_cpu, 0, 2 * n * sizeof(Real));
+    }
+    this->m_mean_density_cpu  = static_cast<Real*>(pinned_alloc(nc * sizeof(Real)));
+    this->m_mean_momentum_cpu = static_cast<Real*>(pinned_alloc(2 * nc * sizeof(Real)));
+    std::memset(this->m_mean_density_cpu, 0, nc * sizeof(Real));
+    std::memset(this->m_mean_momentum_cpu, 0, 2 * nc * sizeof(Real));
+    this->m_node_state_cpu.set_allocator(pinned_alloc, pinned_free);
+    this->m_node_state_cpu.resize(n * 8);
+    // the snapshot lives on the device; the host-side out buffer of the reference is not needed
+    this->m_rnd_cpu.resize(n);
+}
+
+template <Model model_>
+void B200_Lattice<model_>::free_memory()
+{
+    pinned_free(this->m_cell_type_cpu);
+    pinned_free(this->m_cell_density_cpu);
+    pinned_free(this->m_cell_momentum_cpu);
+    pinned_free(this->m_mean_density_cpu);
+    pinned_free(this->m_mean_momentum_cpu);
+    this->m_cell_type_cpu = nullptr;
+    this->m_cell_density_cpu = this->m_cell_momentum_cpu = this->m_mean_density_cpu = this->m_mean_momentum_cpu = nullptr;
+}
+
+template <Model model_>
+void B200_Lattice<model_>::create_device_lattice()
+{
+    lgca_b200_config cfg;
+    std::memset(&cfg, 0, sizeof(cfg));
+    cfg.model     = ModelDescriptor<model_>::C_ABI_ID;
+    cfg.dim_x     = this->m_dim_x;
+    cfg.dim_y     = this->m_dim_y;
+    cfg.cg_radius = this->m_coarse_graining_radius;
+    // the single-collision demo lattice (21 x 10, cg 1) violates dim_x % 2cg == 0 like in the reference
+    if (cfg.cg_radius && (cfg.dim_x % (2 * cfg.cg_radius) || cfg.dim_y % (2 * cfg.cg_radius) || cfg.dim_x < 4 * cfg.cg_radius))
+        cfg.cg_radius = 0;
+    cfg.bf_dir = this->m_bf_dir;
+    cfg.device = m_opt.device;
+    cfg.k_fuse = m_opt.k_fuse;
+    cfg.flags  = m_opt.cell_fields ? 0u : (uint32_t)LGCA_B200_FLAG_NO_CELL_FIELDS;
+    const int rc = lgca_b200_create(&cfg, &m_h);
+    if (rc) fail("B200_Lattice", rc);
+}
+
+template <Model model_>
+void B200_Lattice<model_>::setup_parallel()
+{
+    lgca_b200_info info;
+    const int rc = lgca_b200_get_info(m_h, &info);
+    if (rc) fail("setup_parallel", rc);
+    printf("B200 configuration parameters: device %d, %u bit-planes of %u x %u words, %d fused steps per pass, "
+           "%.1f MB on the device.\n\n", m_opt.device, info.num_planes, info.y_rows, info.words_per_row, info.k_fuse,
+           info.device_bytes / 1.0e6);
+}
+
+template <Model model_>
+void B200_Lattice<model_>::copy_data_to_device()
+{
+    const int rc = lgca_b200_upload(m_h, this->m_node_state_cpu.ptr(), reinterpret_cast<const int32_t*>(this->m_cell_type_cpu),
+                                    this->m_rnd_cpu.ptr());
+    if (rc) fail("copy_data_to_device", rc);
+    m_on_device = true;
+}
+
+template <Model model_>
+void B200_Lattice<model_>::ensure_on_device()
+{
+    if (!m_on_device) copy_data_to_device();
+}
+
+template <Model model_>
+void B200_Lattice<model_>::copy_data_from_device()
+{
+    ensure_on_device();
+    const int rc = lgca_b200_download(m_h, this->m_node_state_cpu.ptr());
+    if (rc) fail("copy_data_from_device", rc);
+}
+
+template <Model model_>
+void B200_Lattice<model_>::collide_and_propagate(const bool /*p: ignored, as in the reference's live backend*/)
+{
+    collide_and_propagate_n(1);
+}
+
+template <Model model_>
+void B200_Lattice<model_>::collide_and_propagate_n(int n_steps)
+{
+    ensure_on_device();
+    const int rc = lgca_b200_step(m_h, n_steps);
+    if (rc) fail("collide_and_propagate", rc);
+}
+
+template <Model model_>
+void B200_Lattice<model_>::copy_data_to_output_buffer()
+{
+    ensure_on_device();
+    const int rc = lgca_b200_snapshot(m_h);
+    if (rc) fail("copy_data_to_output_buffer", rc);
+}
+
+template <Model model_>
+void B200_Lattice<model_>::post_process()
+{
+    ensure_on_device();
+    const bool coarse = this->m_num_coarse_cells > 0 && this->m_dim_x % (2 * this->m_coarse_graining_radius) == 0 &&
+                        this->m_dim_x >= 4 * this->m_coarse_graining_radius;
+    const int rc = lgca_b200_post_process(m_h, this->m_cell_density_cpu, this->m_cell_momentum_cpu,
+                                          coarse ? this->m_mean_density_cpu : nullptr,
+                                          coarse ? this->m_mean_momentum_cpu : nullptr, m_opt.exact_post ? 1 : 0);
+    if (rc) fail("post_process", rc);
+    m_fields_valid = true;
+}
+
+template <Model model_>
+std::vector<Real> B200_Lattice<model_>::get_mean_velocity()
+{
+    std::vector<Real> mean_velocity(this->SPATIAL_DIM, 0.0);
+    if (this->m_cell_density_cpu && m_fields_valid) {
+        // the reference's loop at one thread (src/omp_lattice.cpp:508-557): sequential float32 sums over the
+        // per-cell host fields of the last post_process() -- the only order that reproduces its digits
+        Real sum_x = 0.0, sum_y = 0.0;
+        size_t counter = 0;
+        for (size_t n = 0; n < this->m_num_cells; ++n) {
+            if (this->m_cell_type_cpu[n] != CellType::FLUID) continue;
+            counter++;
+            const Real rho = this->m_cell_density_cpu[n];
+            if (rho > 1.0e-06) {
+                sum_x += this->m_cell_momentum_cpu[2 * n] / rho;
+                sum_y += this->m_cell_momentum_cpu[2 * n + 1] / rho;
+            }
+        }
+        mean_velocity[0] = sum_x / (Real)counter;
+        mean_velocity[1] = sum_y / (Real)counter;
+        return mean_velocity;
+    }
+    // no per-cell host fields (huge lattices): device reduction over the snapshot
+    ensure_on_device();
+    float out[2];
+    const int rc = lgca_b200_mean_velocity(m_h, out);
+    if (rc) fail("get_mean_velocity", rc);
+    mean_velocity[0] = out[0];
+    mean_velocity[1] = out[1];
+    return mean_velocity;
+}
+
+template <Model model_>
+void B200_Lattice<model_>::apply_body_force(const int forcing)
+{
+    ensure_on_device();
+    // The reference draws `rand() % num_cells` one at a time until `forcing` particles are reverted or
+    // 2*num_cells draws are spent (do-while: at least one draw; src/omp_lattice.cpp:254-346).  Here rand() values
+    // are drawn ahead into a FIFO, handed to the device in order, and the unconsumed ones are kept for the next
+    // call, so the stream position after the call equals the reference's as seen by this lattice.
+    const size_t it_max = 2 * this->m_num_cells;
+    size_t it = 0;
+    long   remaining = forcing;
+    bool   first = true;
+    std::vector<int32_t> batch;
+    while ((first || remaining > 0) && it < it_max) {
+        size_t want = (size_t)std::max<double>(256.0, (double)std::max<long>(remaining, 1) * m_draws_per_hit * 1.25);
+        want = std::min(want, it_max - it);
+        while (m_draws.size() < want) m_draws.push_back(std::rand());
+        batch.assign(m_draws.begin(), m_draws.begin() + want);
+        size_t consumed = 0;
+        uint32_t reverted = 0;
+        const int rc = lgca_b200_body_force(m_h, (int)remaining, batch.data(), want, &consumed, &reverted);
+        if (rc) fail("apply_body_force", rc);
+        m_draws.erase(m_draws.begin(), m_draws.begin() + consumed);
+        it += consumed;
+        remaining -= reverted;
+        if (reverted > 0) m_draws_per_hit = 0.5 * m_draws_per_hit + 0.5 * std::min(1.0e4, (double)consumed / reverted);
+        else m_draws_per_hit = std::min(1.0e4, m_draws_per_hit * 2.0);
+        first = false;
+        if (consumed == 0) break;
+    }
+}
+
+template <Model model_>
+unsigned long B200_Lattice<model_>::get_n_particles()
+{
+    if (!m_on_device) return Lattice<model_>::get_n_particles(); // still being set up on the host
+    uint64_t n = 0;
+    const int rc = lgca_b200_count_particles(m_h, &n);
+    if (rc) fail("get_n_particles", rc);
+    this->m_num_particles = n;
+    return n;
+}
+
+template <Model model_>
+void B200_Lattice<model_>::synchronize()
+{
+    const int rc = lgca_b200_sync(m_h);
+    if (rc) fail("synchronize", rc);
+}
+
+template <Model model_>
+double B200_Lattice<model_>::timed_steps(int n_steps)
+{
+    ensure_on_device();
+    float ms = 0;
+    const int rc = lgca_b200_timed_steps(m_h, n_steps, &ms);
+    if (rc) fail("timed_steps", rc);
+    return ms;
+}
+
+template class B200_Lattice<Model::HPP>;
+template class B200_Lattice<Model::FHP_I>;
+template class B200_Lattice<Model::FHP_II>;
+template class B200_Lattice<Model::FHP_III>;
+
+} // namespace lgca

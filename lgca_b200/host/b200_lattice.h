@@ -1,0 +1,74 @@
+// B200_Lattice<Model>: the B200 backend behind the reference's Lattice<Model> interface -- the class an app
+// constructs where it used to say `new OMP_Lattice<MODEL>(...)` (reference: src/omp_lattice.h:29-78,
+// apps/pipe/pipe_viewer.cpp:46).  All lattice arithmetic happens in liblgca_b200.so through the C-ABI
+// (include/lgca_b200.h); this class only owns the host mirrors and keeps the reference's call semantics:
+//
+//   * ctor allocates, then draws the chirality bits (rand() stream order of src/omp_lattice.cpp:74-88);
+//   * BC painters / initialisers of the base class work on the host mirrors; the first device-facing call
+//     (collide_and_propagate, apply_body_force, copy_data_to_output_buffer, post_process, get_n_particles)
+//     uploads them automatically, so apps that never call copy_data_to_device() still work;
+//   * post_process() fills the same four host float arrays (stable pointers, like IoVti expects);
+//   * get_mean_velocity() is the reference's sequential float32 loop over those host fields (bit-exact);
+//   * apply_body_force() feeds the caller's rand() stream, in order, to the exact device body force;
+//   * errors print "ERROR in ..." and abort(), like the reference.
+#ifndef LGCA_B200_HOST_B200_LATTICE_H_
+#define LGCA_B200_HOST_B200_LATTICE_H_
+
+#include <deque>
+
+#include "lattice.h"
+
+struct lgca_b200_lattice;
+
+namespace lgca {
+
+struct B200Options {
+    int  device  = 0;     // CUDA device ordinal
+    int  k_fuse  = 0;     // time steps fused per HBM pass (0 = library default)
+    bool cell_fields = true;  // produce per-cell density/momentum in post_process (needs 12 B/cell host+device)
+    bool exact_post  = true;  // reference summation order for the coarse momentum-y means
+};
+
+template <Model model_>
+class B200_Lattice : public Lattice<model_> {
+public:
+    B200_Lattice(const string test_case, const Real Re, const Real Ma_s, const int coarse_graining_radius,
+                 const B200Options& opt = B200Options());
+    // explicit-dims extension (e.g. the 65536 x 32768 box of BASELINE config C4)
+    B200_Lattice(const string test_case, unsigned int dim_x, unsigned int dim_y, const int coarse_graining_radius,
+                 char bf_dir, const B200Options& opt = B200Options());
+    virtual ~B200_Lattice();
+
+    void setup_parallel() override;
+    void collide_and_propagate(const bool p = false) override;
+    void collide_and_propagate_n(int n_steps);           // n fused updates in one call (extension)
+    std::vector<Real> get_mean_velocity() override;
+    void apply_body_force(const int forcing) override;
+    void post_process() override;
+    void copy_data_to_device() override;
+    void copy_data_from_device() override;
+    void copy_data_to_output_buffer() override;
+    unsigned long get_n_particles() override;
+
+    void   synchronize();
+    double timed_steps(int n_steps);                      // device time [ms] of n updates (CUDA events)
+    lgca_b200_lattice* handle() { return m_h; }
+
+private:
+    void allocate_memory();
+    void free_memory();
+    void create_device_lattice();
+    void ensure_on_device();
+    void fail(const char* where, int rc);
+
+    B200Options        m_opt;
+    lgca_b200_lattice* m_h = nullptr;
+    bool               m_on_device = false;   // host mirrors have been uploaded
+    bool               m_fields_valid = false;
+    std::deque<int>    m_draws;               // rand() values drawn ahead for the body force, in stream order
+    double             m_draws_per_hit = 8.0; // running estimate used to size the draw-ahead
+};
+
+} // namespace lgca
+
+#endif
