@@ -74,7 +74,9 @@ struct WaveState {
     // delay lines of the level transition s-1 -> s (index s-1): planes of the previous row (C*) and
     // planes 1,2 of the row before that (D*)
     uint32_t C0[K], C1[K], C2[K], C3[K], C6[K], D1[K], D2[K];
-    uint32_t nxt[7];                 // prefetched level-0 row
+    uint32_t nxt[7];                 // prefetched level-0 row r0 + 1
+    uint32_t nx2[7];                 // prefetched level-0 row r0 + 2 (loads stay in flight for a whole iteration)
+    uint32_t pm1, pns1, psl1;        // prefetched mask words of row r0 + 1
     uint32_t Mp[K], Mns[K], Msl[K];  // mask words of the rows the levels produce next: index s-1 <-> row r0 - s
     uint32_t r0m;                    // stored index of the level-0 row that arrived last
 };
@@ -92,21 +94,24 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>&
 
     uint32_t a[7];
 #pragma unroll
-    for (int d = 0; d < ND; ++d) a[d] = st.nxt[d];
+    for (int d = 0; d < ND; ++d) { a[d] = st.nxt[d]; st.nxt[d] = st.nx2[d]; }
+    // mask words of the arriving row r0 (prefetched one iteration ago); level 1 uses them next iteration
+    const uint32_t pm = st.pm1, pns = st.pns1, psl = st.psl1;
 
     if (++st.r0m >= rows) st.r0m -= rows; // stored index of the arriving row r0
-    // prefetch the next level-0 row (r0 + 1) and the mask words of row r0 (level 1 needs them next time).
-    // Past the end of the chunk this reads a valid but unneeded row.
-    uint32_t pm = 0u, pns = 0u, psl = 0u;
+    // Prefetch TWO rows ahead: level-0 row r0 + 2 and the mask words of row r0 + 1.  The loads have a whole
+    // iteration to land wherever the scheduler places them.  Past the end of the chunk this reads valid but
+    // unneeded rows.
     {
-        const uint32_t rn = (st.r0m + 1 >= rows) ? st.r0m + 1 - rows : st.r0m + 1;
-        const uint32_t ro = rn * g.pitch;
+        uint32_t r1 = st.r0m + 1; if (r1 >= rows) r1 -= rows;
+        uint32_t r2 = r1 + 1;     if (r2 >= rows) r2 -= rows;
+        const uint32_t ro = r2 * g.pitch;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) st.nxt[d] = src.load(A.in[d], ro);
-        const uint32_t rm = st.r0m * g.pitch;
-        if (!HPP) pm = src.load(A.ch, rm);
-        if (HAS_NS) pns = src.load(A.ns, rm);
-        if (HAS_SL) psl = src.load(A.sl, rm);
+        for (int d = 0; d < ND; ++d) st.nx2[d] = src.load(A.in[d], ro);
+        const uint32_t rm = r1 * g.pitch;
+        if (!HPP) st.pm1 = src.load(A.ch, rm);
+        if (HAS_NS) st.pns1 = src.load(A.ns, rm);
+        if (HAS_SL) st.psl1 = src.load(A.sl, rm);
     }
 #pragma unroll
     for (int s = 1; s <= K; ++s) {
@@ -244,10 +249,16 @@ __global__ void __launch_bounds__(32) step_wave_kernel(const WaveArgs A, const G
     if (r0 < 0) r0 += rows;
     {
         const uint32_t ro = (uint32_t)r0 * g.pitch;
+        const uint32_t r1 = (uint32_t)(r0 + 1 >= rows ? r0 + 1 - rows : r0 + 1);
+        const uint32_t ro1 = r1 * g.pitch;
 #pragma unroll
-        for (int d = 0; d < ND; ++d) st.nxt[d] = src.load(A.in[d], ro);
-#pragma unroll
-        for (int d = ND; d < 7; ++d) st.nxt[d] = 0u;
+        for (int d = 0; d < 7; ++d) {
+            st.nxt[d] = d < ND ? src.load(A.in[d], ro) : 0u;
+            st.nx2[d] = d < ND ? src.load(A.in[d], ro1) : 0u;
+        }
+        st.pm1  = rule_of(MODEL) != MODEL_HPP ? src.load(A.ch, ro) : 0u;
+        st.pns1 = HAS_NS ? src.load(A.ns, ro) : 0u;
+        st.psl1 = HAS_SL ? src.load(A.sl, ro) : 0u;
     }
     st.r0m = (uint32_t)(r0 == 0 ? rows - 1 : r0 - 1); // wave_row advances it to the arriving row first thing
 
