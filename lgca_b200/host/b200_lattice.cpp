@@ -14,6 +14,7 @@ void* pinned_alloc(size_t bytes)
     void* p = nullptr;
     if (lgca_b200_host_alloc(bytes, &p) != 0) {
         printf("ERROR in B200_Lattice::allocate_memory(): %s\n", lgca_b200_last_error());
+        fflush(stdout);
         abort();
     }
     return p;
@@ -25,6 +26,7 @@ template <Model model_>
 void B200_Lattice<model_>::fail(const char* where, int rc)
 {
     printf("ERROR in B200_Lattice::%s(): %s (code %d)\n", where, lgca_b200_last_error(), rc);
+    fflush(stdout);
     abort();
 }
 

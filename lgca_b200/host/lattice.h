@@ -129,6 +129,7 @@ public:
     const int32_t*  cell_types()  const { return reinterpret_cast<const int32_t*>(m_cell_type_cpu); }
     const uint8_t*  rnd_bits()    const { return m_rnd_cpu.ptr(); }
     char            bf_dir()      const { return m_bf_dir; }
+    bool            has_cell_fields() const { return m_cell_density_cpu != nullptr && m_cell_momentum_cpu != nullptr; }
     const string&   test_case()   const { return m_test_case; }
 
 private:
