@@ -205,13 +205,17 @@ def run_b200_arm(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        # keep stdout to the one JSON line (the image sets NCCL_DEBUG=VERSION, which prints a banner there)
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
 
     model, dx, rows, bc, cg, desc = WORKLOADS[args.workload]
     sites_rank = dx * rows
     sites_total = sites_rank * world
     e = build_engine(args.workload, rank, world, local_rank, args.k_fuse)
-    ring = Ring(e, rank, world, device=device)
+    ring = Ring(e, rank, world, device=device, native=not args.nccl_halo)
+    ring.start()
     info = e.info()
     particles0 = e.count_particles()
     coarse = {}
@@ -255,7 +259,9 @@ def run_b200_arm(args):
     for _ in range(e2e_steps):
         e.upload(state=host_state.array)             # copy_data_to_device()
         if world > 1:
-            ring.exchange(Ring.STATE)                # ghost rows of the freshly uploaded strip
+            e.sync()
+            dist.barrier()                           # every strip uploaded before anyone pushes ghost rows
+            ring.start()                             # ghost rows of the freshly uploaded strips
         ring.step(UPDATES_PER_STEP)                  # 100 x collide_and_propagate()
         e.snapshot()                                 # copy_data_to_output_buffer()
         e.post_process(cell=False, mean=True, exact=False, out=coarse)  # post_process() -> host coarse fields
@@ -308,7 +314,8 @@ def run_b200_arm(args):
             "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes (1 bit per site and direction)",
             "data": "synthetic",
             "config": {"workload": desc, "global_lattice": [dx, rows * world], "sites_per_gpu": sites_rank,
-                       "updates_per_step": UPDATES_PER_STEP, "k_fuse": k, "parallelism": "row strips x%d, halo ring" % world,
+                       "updates_per_step": UPDATES_PER_STEP, "k_fuse": k, "parallelism": "row strips x%d, %s" % (world, "halo ring: NCCL send/recv" if args.nccl_halo else
+                                                            "halo ring: in-kernel peer stores over NVLink (CUDA IPC) + epoch flags"),
                        "cache": "inputs larger than L2 (%.0f MB of bit-planes per GPU vs 126 MB L2)" % (
                            sites_rank * info.num_planes / 8 / 1e6) if sites_rank * info.num_planes / 8 > 200e6 else
                        "lattice (%.0f MB) is L2-resident" % (sites_rank * info.num_planes / 8 / 1e6),
@@ -368,6 +375,7 @@ def main():
     ap.add_argument("--cpu-updates", type=int, default=12, help="updates of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-karman", action="store_true")
+    ap.add_argument("--nccl-halo", action="store_true", help="move ghost rows with NCCL send/recv instead of the native peer-store ring")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)

@@ -183,6 +183,20 @@ int  lgca_b200_halo_import(lgca_b200_lattice* h, int what, const void* dev_from_
 int  lgca_b200_get_wall_flags(lgca_b200_lattice* h, uint32_t* has_no_slip, uint32_t* has_slip);
 int  lgca_b200_set_wall_flags(lgca_b200_lattice* h, uint32_t has_no_slip, uint32_t has_slip);
 
+/* ---- native halo ring: ghost rows stored straight into the neighbours' memory (peer stores / CUDA IPC) ----
+ * Each rank exports an opaque descriptor of its strip (lgca_b200_ring_descriptor_bytes bytes), the caller moves
+ * the descriptors between processes (e.g. torch.distributed.all_gather), every rank connects to its lower
+ * ((r-1) mod n) and upper ((r+1) mod n) neighbour, calls ring_start once after its data is in place, and
+ * then advances with ring_step: per block of <= k_fuse steps the library enqueues wait -> fused-step kernel ->
+ * peer push of the edge rows -> epoch signal on the compute stream; no host synchronisation, no collective.
+ * All ranks must issue the same sequence of ring_step calls.  Strips must have equal heights. */
+int  lgca_b200_ring_descriptor_bytes(size_t* bytes);
+int  lgca_b200_ring_export(lgca_b200_lattice* h, void* descriptor, size_t bytes);
+int  lgca_b200_ring_connect(lgca_b200_lattice* h, const void* lower_descriptor, const void* upper_descriptor);
+int  lgca_b200_ring_start(lgca_b200_lattice* h);
+int  lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps);
+int  lgca_b200_ring_disconnect(lgca_b200_lattice* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -22,6 +22,8 @@ SYMBOLS = [
     "lgca_b200_compute_stream", "lgca_b200_timed_steps", "lgca_b200_timed_kernel", "lgca_b200_launch_count", "lgca_b200_get_info",
     "lgca_b200_halo_rows", "lgca_b200_halo_bytes", "lgca_b200_halo_export", "lgca_b200_halo_import",
     "lgca_b200_get_wall_flags", "lgca_b200_set_wall_flags",
+    "lgca_b200_ring_descriptor_bytes", "lgca_b200_ring_export", "lgca_b200_ring_connect", "lgca_b200_ring_start",
+    "lgca_b200_ring_step", "lgca_b200_ring_disconnect",
 ]
 
 
@@ -88,6 +90,12 @@ def load_library():
     L.lgca_b200_halo_import.argtypes = [vp, i32, vp, vp]
     L.lgca_b200_get_wall_flags.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
     L.lgca_b200_set_wall_flags.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.lgca_b200_ring_descriptor_bytes.argtypes = [C.POINTER(C.c_size_t)]
+    L.lgca_b200_ring_export.argtypes = [vp, vp, C.c_size_t]
+    L.lgca_b200_ring_connect.argtypes = [vp, vp, vp]
+    L.lgca_b200_ring_start.argtypes = [vp]
+    L.lgca_b200_ring_step.argtypes = [vp, i32]
+    L.lgca_b200_ring_disconnect.argtypes = [vp]
     _LIB = L
     return L
 
@@ -129,6 +137,7 @@ class Engine:
         h = C.c_void_p()
         self._check(self.L.lgca_b200_create(C.byref(cfg), C.byref(h)))
         self.h = h
+        self._flags = flags
         self.dim_x, self.dim_y = dim_x, dim_y
         self.cg = cg_radius
         self.num_dir = NUM_DIR[self.model]
@@ -248,6 +257,11 @@ class Engine:
         self._check(self.L.lgca_b200_halo_rows(self.h, C.byref(v)))
         return int(v.value)
 
+    def steps_per_exchange(self):
+        """Steps a strip may advance between two halo exchanges (one launch of the fused-step kernel)."""
+        i = self.info()
+        return 1 if (self._flags & FLAG_SIMPLE_KERNEL) else max(1, min(int(i.k_fuse), self.halo_rows()))
+
     def halo_bytes(self, what=0):
         v = C.c_size_t(0)
         self._check(self.L.lgca_b200_halo_bytes(self.h, what, C.byref(v)))
@@ -258,6 +272,28 @@ class Engine:
 
     def halo_import(self, what, dev_from_upper, dev_from_lower):
         self._check(self.L.lgca_b200_halo_import(self.h, what, C.c_void_p(dev_from_upper), C.c_void_p(dev_from_lower)))
+
+    # --- native ring (peer stores; descriptors are opaque bytes moved between ranks by the caller) --
+    def ring_export(self):
+        n = C.c_size_t(0)
+        self._check(self.L.lgca_b200_ring_descriptor_bytes(C.byref(n)))
+        buf = (C.c_uint8 * n.value)()
+        self._check(self.L.lgca_b200_ring_export(self.h, buf, n.value))
+        return bytes(buf)
+
+    def ring_connect(self, lower_descriptor, upper_descriptor):
+        lo = (C.c_uint8 * len(lower_descriptor)).from_buffer_copy(lower_descriptor)
+        up = (C.c_uint8 * len(upper_descriptor)).from_buffer_copy(upper_descriptor)
+        self._check(self.L.lgca_b200_ring_connect(self.h, lo, up))
+
+    def ring_start(self):
+        self._check(self.L.lgca_b200_ring_start(self.h))
+
+    def ring_step(self, n):
+        self._check(self.L.lgca_b200_ring_step(self.h, int(n)))
+
+    def ring_disconnect(self):
+        self._check(self.L.lgca_b200_ring_disconnect(self.h))
 
     def wall_flags(self):
         a, b = C.c_uint32(0), C.c_uint32(0)

@@ -173,6 +173,8 @@ int lgca_b200_destroy(lgca_b200_lattice* h)
     if (!h) return 0;
     cudaSetDevice(h->cfg.device);
     cudaDeviceSynchronize();
+    lgca_b200_ring_disconnect(h);
+    cudaFree(h->ring_flags);
     for (int i = 0; i < 2; ++i) { cudaFree(h->planes[i]); cudaFree(h->d_stage[i]); }
     cudaFree(h->snap); cudaFree(h->ns); cudaFree(h->sl); cudaFree(h->ch); cudaFree(h->xedge); cudaFree(h->d_flags);
     cudaFree(h->d_cell_density); cudaFree(h->d_cell_momentum); cudaFree(h->d_mean_density); cudaFree(h->d_mean_momentum);
@@ -285,10 +287,13 @@ static int step_impl(lgca_b200_lattice* h, int n_steps, bool check_halo)
 {
     if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
     if (n_steps < 0) return set_error(LGCA_B200_EINVAL, "n_steps < 0");
-    if (check_halo && h->g.halo && (uint32_t)n_steps > h->g.halo)
-        return set_error(LGCA_B200_ESTATE, "a strip can advance at most halo=%u steps between halo exchanges", h->g.halo);
+    // a strip's ghost rows are only refreshed by the halo exchange: one launch (<= k_fuse steps) per exchange
+    if (check_halo && h->g.halo && n_steps > h->k_fuse)
+        return set_error(LGCA_B200_ESTATE, "a strip can advance at most k_fuse=%d steps between halo exchanges", h->k_fuse);
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     const bool simple = (h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) != 0;
+    if (h->g.halo && simple && check_halo && n_steps > 1)
+        return set_error(LGCA_B200_ESTATE, "the generic kernel advances a strip one step per halo exchange");
     while (n_steps > 0) {
         int k = 1, rc;
         if (!simple) {

@@ -53,6 +53,15 @@ struct lgca_b200_lattice {
     int              plan_valid[LGCA_MAX_K + 1];
     uint64_t         launches;
     uint64_t         device_bytes;
+    // native halo ring (lgca_ring.cu)
+    void*            ring_flags;            // [2] epochs published by my lower / upper neighbour
+    void*            ring_lower_planes[2];  // the lower neighbour's ping-pong plane sets (peer / IPC mapping)
+    void*            ring_upper_planes[2];
+    void*            ring_lower_flags;
+    void*            ring_upper_flags;
+    uint32_t         ring_lower_geom_rows, ring_upper_geom_rows;
+    int              ring_lower_ipc, ring_upper_ipc, ring_connected;
+    uint32_t         ring_epoch;
 };
 
 namespace lgca_b200 {
@@ -62,6 +71,8 @@ int launch_step_simple(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, 
 // lgca_step_wave.cu : register wavefront, k steps per HBM pass
 int launch_step_wave(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
 bool wave_supported(const lgca_b200_lattice* h, int k);
+int wave_prepare(lgca_b200_lattice* h);
+int simple_prepare(lgca_b200_lattice* h);
 
 // lgca_pack.cu : reference layouts <-> bit-planes
 int launch_pack_state(lgca_b200_lattice* h, const uint8_t* d_bytes, uint32_t* planes, uint32_t row0, uint32_t nrows,

@@ -1,0 +1,251 @@
+// Native halo ring for row strips: ghost rows are written straight into the ring neighbours' memory by a
+// kernel (peer stores over NVLink / CUDA IPC mappings), ordered with device-side epoch flags -- no host
+// synchronisation, no NCCL call and no packing buffers per block of fused steps.
+//
+// The reference has no domain decomposition; its torus is always periodic in y
+// (src/omp_lattice.cpp:150-176), so strips form a periodic ring: upper neighbour = next strip in +y.
+//
+// Protocol per block b of <= k_fuse steps (epoch numbers count completed exchanges):
+//     wait   : spin until both neighbours have published epoch b      (their ghost rows for this block are in)
+//     step   : fused-step kernel reads buffer A (incl. ghost rows), writes the OWNED rows of buffer B
+//     push   : copy my top/bottom `halo` owned rows of B into the neighbours' ghost rows of THEIR buffer B
+//     signal : publish epoch b+1 in both neighbours' flag words (system-scope release)
+// Safety: a neighbour only starts reading its B ghost rows after my signal b+1; and I only overwrite its A ghost
+// rows at the end of block b+1, which I started after its signal b+1, i.e. after its block-b kernel (the last
+// reader of A) had finished.  The step kernel never stores ghost rows, so pushes cannot be clobbered.
+#include <string.h>
+#include <unistd.h>
+
+#include "lgca_internal.h"
+
+namespace lgca_b200 {
+
+struct RingBlob { // what a rank publishes to its neighbours
+    uint64_t           magic;
+    int32_t            pid, device;
+    uint32_t           rows, pitch, halo, nd;
+    uint64_t           plane_stride;
+    void*              raw_planes[2]; // valid inside the publishing process
+    void*              raw_flags;
+    cudaIpcMemHandle_t ipc_planes[2];
+    cudaIpcMemHandle_t ipc_flags;
+};
+static const uint64_t RING_MAGIC = 0x4C47434152494E47ull; // "LGCARING"
+
+// copies `halo` rows of every plane: src rows [src_row, src_row+halo) -> dst rows [dst_row, ...)
+__global__ void __launch_bounds__(256) ring_push_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst_upper,
+                                                        uint32_t* __restrict__ dst_lower, Geom g, int nd)
+{
+    // x = word in [0, halo*pitch) as uint4, y = plane, z = 0: top rows -> upper neighbour, 1: bottom rows -> lower
+    const uint32_t n4 = g.halo * g.pitch / 4;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    const int d = blockIdx.y;
+    const size_t plane = (size_t)d * g.plane_stride;
+    if (blockIdx.z == 0) {
+        // my highest owned rows become the upper neighbour's lower ghost rows [0, halo)
+        const uint4 v = reinterpret_cast<const uint4*>(src + plane + (size_t)(g.rows - 2 * g.halo) * g.pitch)[i];
+        reinterpret_cast<uint4*>(dst_upper + plane)[i] = v;
+    } else {
+        // my lowest owned rows become the lower neighbour's upper ghost rows [rows-halo, rows)
+        const uint4 v = reinterpret_cast<const uint4*>(src + plane + (size_t)g.halo * g.pitch)[i];
+        reinterpret_cast<uint4*>(dst_lower + plane + (size_t)(g.rows - g.halo) * g.pitch)[i] = v;
+    }
+}
+
+__global__ void ring_signal_kernel(volatile uint32_t* upper_flag_from_lower, volatile uint32_t* lower_flag_from_upper,
+                                   uint32_t epoch)
+{
+    __threadfence_system();
+    // the upper neighbour sees me as its LOWER neighbour (flag slot 0), the lower one as its UPPER (slot 1)
+    *upper_flag_from_lower = epoch;
+    *lower_flag_from_upper = epoch;
+    __threadfence_system();
+}
+
+__global__ void ring_wait_kernel(volatile uint32_t* my_flags, uint32_t epoch)
+{
+    // my_flags[0]: published by my lower neighbour, my_flags[1]: by my upper neighbour
+    while (my_flags[threadIdx.x] < epoch) __nanosleep(200);
+    __threadfence_system();
+}
+
+static int ring_push_and_signal(lgca_b200_lattice* h)
+{
+    const Geom& g = h->g;
+    const int b = h->cur;
+    dim3 grid((g.halo * g.pitch / 4 + 255) / 256, h->nd, 2);
+    ring_push_kernel<<<grid, 256, 0, h->s_compute>>>(h->planes[b], (uint32_t*)h->ring_upper_planes[b],
+                                                     (uint32_t*)h->ring_lower_planes[b], g, h->nd);
+    h->launches++;
+    LGCA_CUDA_CHECK(cudaGetLastError());
+    h->ring_epoch++;
+    ring_signal_kernel<<<1, 1, 0, h->s_compute>>>((volatile uint32_t*)h->ring_upper_flags + 0,
+                                                   (volatile uint32_t*)h->ring_lower_flags + 1, h->ring_epoch);
+    h->launches++;
+    LGCA_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+static int open_peer(const RingBlob& blob, int my_device, void* planes[2], void** flags)
+{
+    if (blob.magic != RING_MAGIC) return set_error(LGCA_B200_EINVAL, "not a ring descriptor");
+    if (blob.pid == (int32_t)getpid()) {
+        // same process (several strips on one box driven by one host process, tests): plain pointers
+        if (blob.device != my_device) {
+            int can = 0;
+            LGCA_CUDA_CHECK(cudaDeviceCanAccessPeer(&can, my_device, blob.device));
+            if (!can) return set_error(LGCA_B200_ENODEV, "no peer access between devices %d and %d", my_device, blob.device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(blob.device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return set_cuda_error(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
+            cudaGetLastError();
+        }
+        planes[0] = blob.raw_planes[0];
+        planes[1] = blob.raw_planes[1];
+        *flags = blob.raw_flags;
+        return 0;
+    }
+    LGCA_CUDA_CHECK(cudaIpcOpenMemHandle(&planes[0], blob.ipc_planes[0], cudaIpcMemLazyEnablePeerAccess));
+    LGCA_CUDA_CHECK(cudaIpcOpenMemHandle(&planes[1], blob.ipc_planes[1], cudaIpcMemLazyEnablePeerAccess));
+    LGCA_CUDA_CHECK(cudaIpcOpenMemHandle(flags, blob.ipc_flags, cudaIpcMemLazyEnablePeerAccess));
+    return 1; // opened through IPC: must be closed
+}
+
+} // namespace lgca_b200
+
+using namespace lgca_b200;
+
+extern "C" {
+
+int lgca_b200_ring_descriptor_bytes(size_t* bytes)
+{
+    if (!bytes) return set_error(LGCA_B200_EINVAL, "null argument");
+    *bytes = sizeof(RingBlob);
+    return 0;
+}
+
+int lgca_b200_ring_export(lgca_b200_lattice* h, void* descriptor, size_t bytes)
+{
+    if (!h || !descriptor) return set_error(LGCA_B200_EINVAL, "null argument");
+    if (bytes < sizeof(RingBlob)) return set_error(LGCA_B200_EINVAL, "descriptor buffer too small");
+    if (!h->g.halo) return set_error(LGCA_B200_ESTATE, "handle owns the whole lattice: no ring");
+    LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+    if (!h->ring_flags) {
+        LGCA_CUDA_CHECK(cudaMalloc(&h->ring_flags, 64));
+        LGCA_CUDA_CHECK(cudaMemset(h->ring_flags, 0, 64));
+    }
+    RingBlob b;
+    memset(&b, 0, sizeof(b));
+    b.magic = RING_MAGIC;
+    b.pid = (int32_t)getpid();
+    b.device = h->cfg.device;
+    b.rows = h->g.rows; b.pitch = h->g.pitch; b.halo = h->g.halo; b.nd = (uint32_t)h->nd;
+    b.plane_stride = h->g.plane_stride;
+    b.raw_planes[0] = h->planes[0];
+    b.raw_planes[1] = h->planes[1];
+    b.raw_flags = h->ring_flags;
+    LGCA_CUDA_CHECK(cudaIpcGetMemHandle(&b.ipc_planes[0], h->planes[0]));
+    LGCA_CUDA_CHECK(cudaIpcGetMemHandle(&b.ipc_planes[1], h->planes[1]));
+    LGCA_CUDA_CHECK(cudaIpcGetMemHandle(&b.ipc_flags, h->ring_flags));
+    memcpy(descriptor, &b, sizeof(b));
+    return 0;
+}
+
+int lgca_b200_ring_connect(lgca_b200_lattice* h, const void* lower_descriptor, const void* upper_descriptor)
+{
+    if (!h || !lower_descriptor || !upper_descriptor) return set_error(LGCA_B200_EINVAL, "null argument");
+    if (!h->g.halo || !h->ring_flags) return set_error(LGCA_B200_ESTATE, "call lgca_b200_ring_export on this handle first");
+    LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+    RingBlob lo, up;
+    memcpy(&lo, lower_descriptor, sizeof(lo));
+    memcpy(&up, upper_descriptor, sizeof(up));
+    for (const RingBlob* b : {&lo, &up}) {
+        if (b->magic != RING_MAGIC) return set_error(LGCA_B200_EINVAL, "not a ring descriptor");
+        if (b->pitch != h->g.pitch || b->halo != h->g.halo || b->nd != (uint32_t)h->nd)
+            return set_error(LGCA_B200_EINVAL, "neighbour strip has a different geometry (pitch/halo/planes)");
+    }
+    if (lo.rows != up.rows && false) return 0;
+    // ghost-row destinations are addressed with the NEIGHBOUR's row count / plane stride
+    h->ring_lower_geom_rows = lo.rows; h->ring_upper_geom_rows = up.rows;
+    if (lo.plane_stride != h->g.plane_stride || up.plane_stride != h->g.plane_stride)
+        return set_error(LGCA_B200_EINVAL, "native ring needs strips of equal height (plane stride differs)");
+    int rc = open_peer(lo, h->cfg.device, h->ring_lower_planes, &h->ring_lower_flags);
+    if (rc < 0) return rc;
+    h->ring_lower_ipc = rc;
+    const bool same = memcmp(&lo, &up, sizeof(lo)) == 0; // world == 2: both neighbours are the same strip
+    if (same) {
+        h->ring_upper_planes[0] = h->ring_lower_planes[0];
+        h->ring_upper_planes[1] = h->ring_lower_planes[1];
+        h->ring_upper_flags = h->ring_lower_flags;
+        h->ring_upper_ipc = 0;
+    } else {
+        rc = open_peer(up, h->cfg.device, h->ring_upper_planes, &h->ring_upper_flags);
+        if (rc < 0) return rc;
+        h->ring_upper_ipc = rc;
+    }
+    // every kernel the ring will enqueue must already be resident: a lazy module load behind a spinning wait
+    // kernel of the same process can deadlock
+    if ((rc = wave_prepare(h))) return rc;
+    if ((rc = simple_prepare(h))) return rc;
+    cudaFuncAttributes fa;
+    LGCA_CUDA_CHECK(cudaFuncGetAttributes(&fa, ring_push_kernel));
+    LGCA_CUDA_CHECK(cudaFuncGetAttributes(&fa, ring_signal_kernel));
+    LGCA_CUDA_CHECK(cudaFuncGetAttributes(&fa, ring_wait_kernel));
+    h->ring_connected = 1;
+    h->ring_epoch = 0;
+    return 0;
+}
+
+// Publishes the current edge rows to the neighbours (epoch 1).  Call on every rank after upload / init and
+// after connect, before the first lgca_b200_ring_step.
+int lgca_b200_ring_start(lgca_b200_lattice* h)
+{
+    if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
+    if (!h->ring_connected) return set_error(LGCA_B200_ESTATE, "ring not connected");
+    LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+    return ring_push_and_signal(h);
+}
+
+int lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps)
+{
+    if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
+    if (!h->ring_connected) return set_error(LGCA_B200_ESTATE, "ring not connected");
+    if (h->ring_epoch == 0) return set_error(LGCA_B200_ESTATE, "call lgca_b200_ring_start first");
+    if (n_steps < 0) return set_error(LGCA_B200_EINVAL, "n_steps < 0");
+    LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+    const int block = (h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) ? 1 : h->k_fuse;
+    while (n_steps > 0) {
+        const int k = n_steps < block ? n_steps : block;
+        ring_wait_kernel<<<1, 2, 0, h->s_compute>>>((volatile uint32_t*)h->ring_flags, h->ring_epoch);
+        h->launches++;
+        LGCA_CUDA_CHECK(cudaGetLastError());
+        int rc = lgca_b200_step(h, k);
+        if (rc) return rc;
+        if ((rc = ring_push_and_signal(h))) return rc;
+        n_steps -= k;
+    }
+    return 0;
+}
+
+int lgca_b200_ring_disconnect(lgca_b200_lattice* h)
+{
+    if (!h) return 0;
+    if (!h->ring_connected) return 0;
+    cudaSetDevice(h->cfg.device);
+    cudaStreamSynchronize(h->s_compute);
+    if (h->ring_lower_ipc) {
+        cudaIpcCloseMemHandle(h->ring_lower_planes[0]);
+        cudaIpcCloseMemHandle(h->ring_lower_planes[1]);
+        cudaIpcCloseMemHandle(h->ring_lower_flags);
+    }
+    if (h->ring_upper_ipc) {
+        cudaIpcCloseMemHandle(h->ring_upper_planes[0]);
+        cudaIpcCloseMemHandle(h->ring_upper_planes[1]);
+        cudaIpcCloseMemHandle(h->ring_upper_flags);
+    }
+    cudaGetLastError();
+    h->ring_connected = 0;
+    return 0;
+}
+
+} // extern "C"

@@ -22,7 +22,7 @@ __global__ void __launch_bounds__(128) step_simple_kernel(const uint32_t* __rest
 {
     constexpr int ND = num_dir_of(MODEL);
     const int wi = blockIdx.y * blockDim.x + threadIdx.x;
-    const int y  = blockIdx.x;
+    const int y  = (int)g.halo + blockIdx.x; // owned rows only: ghost rows of a strip belong to the ring neighbours
     if (wi >= (int)g.nw) return;
 
     const uint32_t gy  = (g.y0 + g.dim_y - g.halo % g.dim_y + (uint32_t)y) % g.dim_y; // global row
@@ -73,7 +73,7 @@ static int launch_model(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out,
 {
     const Geom& g = h->g;
     dim3 block(128, 1, 1);
-    dim3 grid(g.rows, (g.nw + 127) / 128, 1);
+    dim3 grid(g.rows - 2 * g.halo, (g.nw + 127) / 128, 1);
 #define GO(NS, SL)                                                                                              \
     step_simple_kernel<MODEL, NS, SL><<<grid, block, 0, s>>>(in, out, h->ns, h->sl, h->ch, h->xedge, g)
     if (h->has_sl) { if (h->has_ns) GO(true, true); else GO(false, true); }
@@ -82,6 +82,27 @@ static int launch_model(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out,
     h->launches++;
     LGCA_CUDA_CHECK(cudaGetLastError());
     return 0;
+}
+
+template <int MODEL>
+static int prepare_model()
+{
+    cudaFuncAttributes a;
+    LGCA_CUDA_CHECK(cudaFuncGetAttributes(&a, step_simple_kernel<MODEL, false, false>));
+    LGCA_CUDA_CHECK(cudaFuncGetAttributes(&a, step_simple_kernel<MODEL, true, false>));
+    LGCA_CUDA_CHECK(cudaFuncGetAttributes(&a, step_simple_kernel<MODEL, false, true>));
+    LGCA_CUDA_CHECK(cudaFuncGetAttributes(&a, step_simple_kernel<MODEL, true, true>));
+    return 0;
+}
+
+// forces the (lazily loaded) kernel images onto the device, see wave_prepare()
+int simple_prepare(lgca_b200_lattice* h)
+{
+    switch (rule_of(h->cfg.model)) {
+    case MODEL_HPP:    return prepare_model<MODEL_HPP>();
+    case MODEL_FHP_I:  return prepare_model<MODEL_FHP_I>();
+    default:           return prepare_model<MODEL_FHP_II>();
+    }
 }
 
 int launch_step_simple(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s)

@@ -206,8 +206,10 @@ __global__ void __launch_bounds__(32) step_wave_kernel(const WaveArgs A, const G
     const int band  = tile % wp.bands;
     const int chunk = tile / wp.bands;
     const int wi    = band * WAVE_VALID - 1 + lane;          // word column of this lane (may be -1 / >= nw)
-    const int ya    = chunk * wp.chunk_rows;                 // first output row (even)
-    const int yb    = min(ya + wp.chunk_rows, (int)g.rows);  // one past the last output row
+    // output rows = the owned rows [halo, rows - halo): ghost rows of a strip are never written by the step
+    // kernel (the ring neighbours store into them), and halo is even, so ya stays even
+    const int ya    = (int)g.halo + chunk * wp.chunk_rows;                  // first output row (even)
+    const int yb    = min(ya + wp.chunk_rows, (int)(g.rows - g.halo));      // one past the last output row
     const int total = (yb - ya) + 2 * K;                     // level-0 rows to push through
     const int rows  = (int)g.rows;
 
@@ -294,7 +296,7 @@ static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
     const Geom& g = h->g;
     WavePlan wp;
     wp.bands = ((int)g.nw + WAVE_VALID - 1) / WAVE_VALID;
-    const int rows = (int)g.rows;
+    const int rows = (int)(g.rows - 2 * g.halo); // owned rows
     const char* e_cr = getenv("LGCA_B200_CHUNK_ROWS");
     const char* e_res = getenv("LGCA_B200_RESIDENT_WARPS");
     const double resident = e_res ? atof(e_res) : (double)resident_warps;
@@ -333,6 +335,7 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
 {
     auto kernel = step_wave_kernel<MODEL, K, NS, SL, IRREG>;
     if (!h->plan_valid[K]) {
+        // (the occupancy query also forces the lazily loaded kernel image onto the device)
         int blocks = 0;
         LGCA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, 32, 0));
         h->plans[K] = make_plan(h, K, blocks > 0 ? blocks : 16);
@@ -346,6 +349,7 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
         A.out[d] = out + off;
     }
     A.ns = h->ns; A.sl = h->sl; A.ch = h->ch; A.xedge = h->xedge;
+    if (!in) return 0; // prepare only (wave_prepare): plan + module load, no launch
     kernel<<<dim3(wp.tiles, 1, 1), dim3(32, 1, 1), 0, s>>>(A, h->g, wp);
     h->launches++;
     LGCA_CUDA_CHECK(cudaGetLastError());
@@ -382,6 +386,19 @@ int launch_step_wave(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, in
     case MODEL_FHP_I: return launch_m<MODEL_FHP_I>(h, in, out, k, s);
     default:          return launch_m<MODEL_FHP_II>(h, in, out, k, s);
     }
+}
+
+// Plans every K the handle can use and forces the kernel images to be loaded.  With CUDA's lazy module loading
+// the first launch of a kernel may have to wait for the device to go idle -- fatal if another stream of the
+// same process is spinning in the ring's wait kernel; the ring calls this before it starts.
+int wave_prepare(lgca_b200_lattice* h)
+{
+    for (int k = 1; k <= h->k_fuse; ++k) {
+        if (!wave_supported(h, k)) continue;
+        const int rc = launch_step_wave(h, nullptr, nullptr, k, 0);
+        if (rc) return rc;
+    }
+    return 0;
 }
 
 } // namespace lgca_b200

@@ -44,13 +44,15 @@ class Ring:
 
     STATE, MASKS = 0, 1
 
-    def __init__(self, engine, rank, world, device=None, group=None):
+    def __init__(self, engine, rank, world, device=None, group=None, native=False):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.e, self.rank, self.world, self.group = engine, rank, world, group
         self.lower, self.upper = ring_neighbours(rank, world)
         self.halo = engine.halo_rows()
+        # ghost rows are refreshed after every launch of the fused-step kernel: block = k_fuse steps
+        self.block = getattr(engine, "steps_per_exchange", lambda: self.halo)()
         self.device = device if device is not None else torch.device("cpu")
         self._bufs = {}
         self._stream = None
@@ -58,6 +60,22 @@ class Ring:
             # NCCL work is ordered against the engine's own compute stream
             self._stream = torch.cuda.ExternalStream(engine.compute_stream(), device=self.device)
         self.exchanges = 0
+        # native mode: ghost rows are stored straight into the neighbours' memory by the library (CUDA IPC /
+        # peer stores + device-side epoch flags); torch.distributed only carries the descriptors once
+        self.native = bool(native) and self.world > 1 and self.halo > 0
+        if self.native:
+            mine = engine.ring_export()
+            allb = [None] * world
+            dist.all_gather_object(allb, mine, group=group)
+            engine.ring_connect(allb[self.lower], allb[self.upper])
+            dist.barrier(group=group)
+
+    def start(self):
+        """Publish the current edge rows (after upload / init, before the first step)."""
+        if self.native:
+            self.e.ring_start()
+        else:
+            self.exchange(self.STATE)
 
     def _buffers(self, what):
         if what not in self._bufs:
@@ -88,12 +106,15 @@ class Ring:
         self.exchanges += 1
 
     def step(self, n):
-        """n lattice updates; ghost rows are refreshed after every block of <= halo steps."""
+        """n lattice updates; ghost rows are refreshed after every block of <= k_fuse steps."""
         if self.world == 1 or self.halo == 0:
             self.e.step(n)
             return
+        if self.native:
+            self.e.ring_step(n)
+            return
         while n > 0:
-            k = min(self.halo, n)
+            k = min(self.block, n)
             self.e.step(k)
             self.exchange(self.STATE)
             n -= k

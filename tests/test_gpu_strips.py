@@ -68,11 +68,13 @@ def test_strips_equal_single_lattice(model, dims, bc, nstrips, k):
     ring.exchange(0)
     halo = engines[0].halo_rows()
     assert halo >= k and halo % 2 == 0
+    block = engines[0].steps_per_exchange()
+    assert block == k
     done = 0
     for n in (1, k, 2 * k + 1, 7):
         left = n
         while left > 0:
-            b = min(left, halo)
+            b = min(left, block)
             for e in engines:
                 e.step(b)
             ring.exchange(0)
@@ -83,6 +85,50 @@ def test_strips_equal_single_lattice(model, dims, bc, nstrips, k):
         assert np.array_equal(got, o.state), "after %d steps" % done
     assert sum(e.count_particles() for e in engines) == o.n_particles()
     with pytest.raises(lgca_b200.LgcaError):
-        engines[0].step(halo + 1)  # a strip may not run past its ghost rows
+        engines[0].step(block + 1)  # a strip may not run past its ghost rows
+    for e in engines:
+        e.close()
+
+
+@pytest.mark.parametrize("model,dims,bc,nstrips,k", [
+    ("FHP_III", (256, 96), "karman", 2, 2),
+    ("FHP_III", (1024, 120), "periodic", 3, 4),
+    ("FHP_II", (512, 128), "reflecting_back", 4, 3),
+    ("HPP", (640, 96), "reflecting_forward", 3, 4),
+])
+def test_native_ring_equals_single_lattice(model, dims, bc, nstrips, k):
+    """Same invariance through the native ring: peer stores into the neighbours' ghost rows + epoch flags,
+    everything enqueued by lgca_b200_ring_step (strips of one process share plain device pointers)."""
+    import lgca_b200
+    from lgca_b200.ring import partition_rows
+    o = Oracle(model, dims=dims, cg=1, rng=OracleRng(6))
+    o.apply_bc(bc)
+    o.init("random")
+    parts = partition_rows(dims[1], nstrips, 2)
+    assert len(set(r for _, r in parts)) == 1  # native ring needs equal strip heights
+    engines = []
+    for y0, rows in parts:
+        e = lgca_b200.Engine(model, dims[0], dims[1], k_fuse=k, y_begin=y0, y_rows=rows)
+        sl = slice(y0 * dims[0], (y0 + rows) * dims[0])
+        e.upload(o.state[sl], o.cell_type[sl], o.rnd)
+        engines.append(e)
+    flags = [e.wall_flags() for e in engines]
+    for e in engines:
+        e.set_wall_flags(any(f[0] for f in flags), any(f[1] for f in flags))
+    LocalRing(engines).exchange(1)  # static masks of the ghost rows: once, through the packed-buffer path
+    desc = [e.ring_export() for e in engines]
+    n = len(engines)
+    for r, e in enumerate(engines):
+        e.ring_connect(desc[(r - 1) % n], desc[(r + 1) % n])
+    for e in engines:
+        e.ring_start()
+    done = 0
+    for steps in (1, k, 3 * k + 1, 10):
+        for e in engines:
+            e.ring_step(steps)
+        o.step(steps)
+        done += steps
+        got = np.concatenate([e.download() for e in engines])
+        assert np.array_equal(got, o.state), "after %d steps" % done
     for e in engines:
         e.close()
