@@ -46,7 +46,9 @@ def _stale():
 def build_library(force=False, verbose=False):
     if not force and not _stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + sources()
+    extra = os.environ.get("LGCA_B200_NVCC_EXTRA", "").split()  # A/B experiments only
+    out = os.environ.get("LGCA_B200_OUT", LIB)
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + sources()
     env = dict(os.environ)
     env.pop("CXX", None)
     env.pop("CC", None)

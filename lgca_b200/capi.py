@@ -45,7 +45,8 @@ class Info(C.Structure):
 
 
 def library_path():
-    return os.path.join(HERE, "liblgca_b200.so")
+    # LGCA_B200_LIB: alternative build of the same library (A/B experiments); never a different backend
+    return os.environ.get("LGCA_B200_LIB") or os.path.join(HERE, "liblgca_b200.so")
 
 
 _LIB = None

@@ -521,6 +521,7 @@ int lgca_b200_sync(lgca_b200_lattice* h)
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
     LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_post));
+    if (h->s_ring) LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_ring));
     return 0;
 }
 

@@ -62,6 +62,10 @@ struct lgca_b200_lattice {
     uint32_t         ring_lower_geom_rows, ring_upper_geom_rows;
     int              ring_lower_ipc, ring_upper_ipc, ring_connected;
     uint32_t         ring_epoch;
+    uint64_t         ring_blocks;           // blocks issued since ring_start
+    uint32_t         ring_inkernel_epoch;   // != 0: the next wave launch waits in-kernel for this epoch
+    cudaStream_t     s_ring;                // pushes + signals run here, overlapped with the next step kernel
+    cudaEvent_t      ev_step[2], ev_push[2];
 };
 
 namespace lgca_b200 {

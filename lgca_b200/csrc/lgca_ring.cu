@@ -70,18 +70,19 @@ __global__ void ring_wait_kernel(volatile uint32_t* my_flags, uint32_t epoch)
     __threadfence_system();
 }
 
-static int ring_push_and_signal(lgca_b200_lattice* h)
+// push my edge rows of the live buffer to the neighbours and publish the next epoch, on stream `s`
+static int ring_push_and_signal(lgca_b200_lattice* h, cudaStream_t s)
 {
     const Geom& g = h->g;
     const int b = h->cur;
     dim3 grid((g.halo * g.pitch / 4 + 255) / 256, h->nd, 2);
-    ring_push_kernel<<<grid, 256, 0, h->s_compute>>>(h->planes[b], (uint32_t*)h->ring_upper_planes[b],
-                                                     (uint32_t*)h->ring_lower_planes[b], g, h->nd);
+    ring_push_kernel<<<grid, 256, 0, s>>>(h->planes[b], (uint32_t*)h->ring_upper_planes[b], (uint32_t*)h->ring_lower_planes[b],
+                                          g, h->nd);
     h->launches++;
     LGCA_CUDA_CHECK(cudaGetLastError());
     h->ring_epoch++;
-    ring_signal_kernel<<<1, 1, 0, h->s_compute>>>((volatile uint32_t*)h->ring_upper_flags + 0,
-                                                   (volatile uint32_t*)h->ring_lower_flags + 1, h->ring_epoch);
+    ring_signal_kernel<<<1, 1, 0, s>>>((volatile uint32_t*)h->ring_upper_flags + 0, (volatile uint32_t*)h->ring_lower_flags + 1,
+                                       h->ring_epoch);
     h->launches++;
     LGCA_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -133,6 +134,11 @@ int lgca_b200_ring_export(lgca_b200_lattice* h, void* descriptor, size_t bytes)
     if (!h->ring_flags) {
         LGCA_CUDA_CHECK(cudaMalloc(&h->ring_flags, 64));
         LGCA_CUDA_CHECK(cudaMemset(h->ring_flags, 0, 64));
+        LGCA_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_ring, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; ++i) {
+            LGCA_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming));
+            LGCA_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_push[i], cudaEventDisableTiming));
+        }
     }
     RingBlob b;
     memset(&b, 0, sizeof(b));
@@ -203,7 +209,13 @@ int lgca_b200_ring_start(lgca_b200_lattice* h)
     if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
     if (!h->ring_connected) return set_error(LGCA_B200_ESTATE, "ring not connected");
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
-    return ring_push_and_signal(h);
+    // everything queued so far (upload, init, earlier ring traffic) precedes the first push
+    LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_ring));
+    int rc = ring_push_and_signal(h, h->s_compute);
+    if (rc) return rc;
+    LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
+    h->ring_blocks = 0;
+    return 0;
 }
 
 int lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps)
@@ -213,15 +225,32 @@ int lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps)
     if (h->ring_epoch == 0) return set_error(LGCA_B200_ESTATE, "call lgca_b200_ring_start first");
     if (n_steps < 0) return set_error(LGCA_B200_EINVAL, "n_steps < 0");
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
-    const int block = (h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) ? 1 : h->k_fuse;
+    const bool simple = (h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) != 0;
+    const int block = simple ? 1 : h->k_fuse;
     while (n_steps > 0) {
         const int k = n_steps < block ? n_steps : block;
-        ring_wait_kernel<<<1, 2, 0, h->s_compute>>>((volatile uint32_t*)h->ring_flags, h->ring_epoch);
-        h->launches++;
-        LGCA_CUDA_CHECK(cudaGetLastError());
-        int rc = lgca_b200_step(h, k);
+        const int slot = (int)(h->ring_blocks & 1u);
+        // (WAR) this block overwrites the edge rows that the push two blocks ago read
+        if (h->ring_blocks >= 2) LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_push[slot], 0));
+        int rc;
+        if (!simple && wave_supported(h, k)) {
+            // tiles that read ghost rows wait in-kernel; the rest of the strip starts immediately
+            h->ring_inkernel_epoch = h->ring_epoch;
+            rc = lgca_b200_step(h, k);
+            h->ring_inkernel_epoch = 0;
+        } else {
+            ring_wait_kernel<<<1, 2, 0, h->s_compute>>>((volatile uint32_t*)h->ring_flags, h->ring_epoch);
+            h->launches++;
+            LGCA_CUDA_CHECK(cudaGetLastError());
+            rc = lgca_b200_step(h, k);
+        }
         if (rc) return rc;
-        if ((rc = ring_push_and_signal(h))) return rc;
+        // push + signal overlap with the next block's interior tiles
+        LGCA_CUDA_CHECK(cudaEventRecord(h->ev_step[slot], h->s_compute));
+        LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_ring, h->ev_step[slot], 0));
+        if ((rc = ring_push_and_signal(h, h->s_ring))) return rc;
+        LGCA_CUDA_CHECK(cudaEventRecord(h->ev_push[slot], h->s_ring));
+        h->ring_blocks++;
         n_steps -= k;
     }
     return 0;
@@ -233,6 +262,7 @@ int lgca_b200_ring_disconnect(lgca_b200_lattice* h)
     if (!h->ring_connected) return 0;
     cudaSetDevice(h->cfg.device);
     cudaStreamSynchronize(h->s_compute);
+    if (h->s_ring) cudaStreamSynchronize(h->s_ring);
     if (h->ring_lower_ipc) {
         cudaIpcCloseMemHandle(h->ring_lower_planes[0]);
         cudaIpcCloseMemHandle(h->ring_lower_planes[1]);

@@ -46,7 +46,17 @@ struct WaveArgs {
     const uint32_t* sl;
     const uint32_t* ch;
     const uint32_t* xedge;
+    // native ring: tiles that read ghost rows spin until the neighbours have published `ring_epoch`
+    const uint32_t* ring_flags; // [0] from the lower neighbour, [1] from the upper; nullptr = no in-kernel wait
+    uint32_t        ring_epoch;
 };
+
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
 
 // Per-lane view of the periodic row: where this lane's 32 sites come from.
 template <bool IRREG>
@@ -57,6 +67,9 @@ struct LaneSrc {
     // row_off = word offset of the row start inside a plane
     __device__ __forceinline__ uint32_t load(const uint32_t* __restrict__ plane, uint32_t row_off) const
     {
+        // Read-only path (ld.global.nc): neighbouring bands share two words per row through L1.  Safe next to the
+        // ring's in-kernel arrival of ghost rows because no tile ever touches a ghost row it does not need
+        // (the prefetch is clamped to the tile's input rows) and tiles that need them wait for the flag first.
         uint32_t v = __ldg(plane + (row_off + wa));
         if (IRREG) {
             if (!regular) { // lanes at the row end of a width that is not a multiple of 32
@@ -79,6 +92,7 @@ struct WaveState {
     uint32_t pm1, pns1, psl1;        // prefetched mask words of row r0 + 1
     uint32_t Mp[K], Mns[K], Msl[K];  // mask words of the rows the levels produce next: index s-1 <-> row r0 - s
     uint32_t r0m;                    // stored index of the level-0 row that arrived last
+    uint32_t pf, pf_left;            // stored index of the last level-0 row fetched / rows still to fetch
 };
 
 // One iteration: level-0 row r0 arrives, every level s produces its row r0 - s, and the level-K row
@@ -100,12 +114,13 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>&
 
     if (++st.r0m >= rows) st.r0m -= rows; // stored index of the arriving row r0
     // Prefetch TWO rows ahead: level-0 row r0 + 2 and the mask words of row r0 + 1.  The loads have a whole
-    // iteration to land wherever the scheduler places them.  Past the end of the chunk this reads valid but
-    // unneeded rows.
+    // iteration to land wherever the scheduler places them.
     {
         uint32_t r1 = st.r0m + 1; if (r1 >= rows) r1 -= rows;
-        uint32_t r2 = r1 + 1;     if (r2 >= rows) r2 -= rows;
-        const uint32_t ro = r2 * g.pitch;
+        // never fetch past the tile's last input row (the last fetch is simply repeated): ghost rows of a strip
+        // are only ever read by tiles that waited for them
+        if (st.pf_left) { --st.pf_left; if (++st.pf >= rows) st.pf -= rows; }
+        const uint32_t ro = st.pf * g.pitch;
 #pragma unroll
         for (int d = 0; d < ND; ++d) st.nx2[d] = src.load(A.in[d], ro);
         const uint32_t rm = r1 * g.pitch;
@@ -204,7 +219,26 @@ __global__ void __launch_bounds__(32) step_wave_kernel(const WaveArgs A, const G
     // shuffles in the row loop compile to plain SHFL without convergence bookkeeping
     const int tile = blockIdx.x;
     const int band  = tile % wp.bands;
-    const int chunk = tile / wp.bands;
+    int chunk = tile / wp.bands;
+    if (g.halo) {
+        // strips: the two chunks that read ghost rows are scheduled first (0 -> bottom chunk, 1 -> top chunk) so
+        // that the edge rows are finished -- and can be pushed to the neighbours -- as early as possible
+        chunk = chunk == 0 ? 0 : (chunk == 1 ? wp.chunks - 1 : chunk - 1);
+        if (A.ring_flags) {
+            // in-kernel halo wait: only tiles whose input rows [ya-K, yb+K) reach into the ghost rows depend on the
+            // neighbours' pushes (a short last chunk makes the one below it depend on them too); the rest start at once
+            const int cya = (int)g.halo + chunk * wp.chunk_rows;
+            const int cyb = min(cya + wp.chunk_rows, (int)(g.rows - g.halo));
+            const bool need_lo = cya - K < (int)g.halo, need_hi = cyb + K > (int)(g.rows - g.halo);
+            if (need_lo || need_hi) {
+                if (lane == 0) {
+                    if (need_lo) while (ld_acquire_sys(A.ring_flags + 0) < A.ring_epoch) __nanosleep(64);
+                    if (need_hi) while (ld_acquire_sys(A.ring_flags + 1) < A.ring_epoch) __nanosleep(64);
+                }
+                __syncwarp();
+            }
+        }
+    }
     const int wi    = band * WAVE_VALID - 1 + lane;          // word column of this lane (may be -1 / >= nw)
     // output rows = the owned rows [halo, rows - halo): ghost rows of a strip are never written by the step
     // kernel (the ring neighbours store into them), and halo is even, so ya stays even
@@ -263,6 +297,8 @@ __global__ void __launch_bounds__(32) step_wave_kernel(const WaveArgs A, const G
         st.psl1 = HAS_SL ? src.load(A.sl, ro) : 0u;
     }
     st.r0m = (uint32_t)(r0 == 0 ? rows - 1 : r0 - 1); // wave_row advances it to the arriving row first thing
+    st.pf = (uint32_t)(r0 + 1 >= rows ? r0 + 1 - rows : r0 + 1);
+    st.pf_left = (uint32_t)(total - 2);
 
     // word offset of the row stored by the current iteration (row ya - 2K + jc), advanced per row
     uint32_t out_off = (uint32_t)ya * g.pitch + (uint32_t)max(wi, 0);
@@ -349,6 +385,8 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
         A.out[d] = out + off;
     }
     A.ns = h->ns; A.sl = h->sl; A.ch = h->ch; A.xedge = h->xedge;
+    A.ring_flags = h->ring_inkernel_epoch ? (const uint32_t*)h->ring_flags : nullptr;
+    A.ring_epoch = h->ring_inkernel_epoch;
     if (!in) return 0; // prepare only (wave_prepare): plan + module load, no launch
     kernel<<<dim3(wp.tiles, 1, 1), dim3(32, 1, 1), 0, s>>>(A, h->g, wp);
     h->launches++;
