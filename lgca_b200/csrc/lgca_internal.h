@@ -14,6 +14,7 @@ namespace lgca_b200 {
 struct WavePlan {
     int bands;      // 30-word bands per row
     int chunk_rows; // output rows per chunk (even)
+    int edge_rows;  // strips: rows of the bottom / top edge chunk (0 = uniform chunks)
     int chunks;     // chunks over the stored rows
     int tiles;      // bands * chunks = warps launched
 };
@@ -76,6 +77,7 @@ int launch_step_simple(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, 
 int launch_step_wave(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
 bool wave_supported(const lgca_b200_lattice* h, int k);
 int wave_prepare(lgca_b200_lattice* h);
+bool wave_has_edge_chunks(lgca_b200_lattice* h, int k);
 int simple_prepare(lgca_b200_lattice* h);
 
 // lgca_pack.cu : reference layouts <-> bit-planes

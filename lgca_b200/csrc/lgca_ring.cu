@@ -13,6 +13,7 @@
 // Safety: a neighbour only starts reading its B ghost rows after my signal b+1; and I only overwrite its A ghost
 // rows at the end of block b+1, which I started after its signal b+1, i.e. after its block-b kernel (the last
 // reader of A) had finished.  The step kernel never stores ghost rows, so pushes cannot be clobbered.
+#include <stdlib.h>
 #include <string.h>
 #include <unistd.h>
 
@@ -134,7 +135,11 @@ int lgca_b200_ring_export(lgca_b200_lattice* h, void* descriptor, size_t bytes)
     if (!h->ring_flags) {
         LGCA_CUDA_CHECK(cudaMalloc(&h->ring_flags, 64));
         LGCA_CUDA_CHECK(cudaMemset(h->ring_flags, 0, 64));
-        LGCA_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_ring, cudaStreamNonBlocking));
+        // highest priority: the tiny push/signal kernels must be dispatched ahead of the next step kernel's blocks,
+        // which become ready at the same moment and would otherwise fill every SM first
+        int prio_lo = 0, prio_hi = 0;
+        LGCA_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+        LGCA_CUDA_CHECK(cudaStreamCreateWithPriority(&h->s_ring, cudaStreamNonBlocking, prio_hi));
         for (int i = 0; i < 2; ++i) {
             LGCA_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_step[i], cudaEventDisableTiming));
             LGCA_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_push[i], cudaEventDisableTiming));
@@ -227,15 +232,18 @@ int lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps)
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     const bool simple = (h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) != 0;
     const int block = simple ? 1 : h->k_fuse;
+    // timing experiments only (results are wrong with these): 1 = no ghost-row wait, 2 = no push/signal, 3 = neither
+    static int dbg = -1;
+    if (dbg < 0) { const char* e = getenv("LGCA_B200_RING_DEBUG"); dbg = e ? atoi(e) : 0; }
     while (n_steps > 0) {
         const int k = n_steps < block ? n_steps : block;
         const int slot = (int)(h->ring_blocks & 1u);
         // (WAR) this block overwrites the edge rows that the push two blocks ago read
         if (h->ring_blocks >= 2) LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_push[slot], 0));
         int rc;
-        if (!simple && wave_supported(h, k)) {
+        if (!simple && wave_has_edge_chunks(h, k)) {
             // tiles that read ghost rows wait in-kernel; the rest of the strip starts immediately
-            h->ring_inkernel_epoch = h->ring_epoch;
+            h->ring_inkernel_epoch = (dbg & 1) ? 0 : h->ring_epoch;
             rc = lgca_b200_step(h, k);
             h->ring_inkernel_epoch = 0;
         } else {
@@ -248,7 +256,8 @@ int lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps)
         // push + signal overlap with the next block's interior tiles
         LGCA_CUDA_CHECK(cudaEventRecord(h->ev_step[slot], h->s_compute));
         LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_ring, h->ev_step[slot], 0));
-        if ((rc = ring_push_and_signal(h, h->s_ring))) return rc;
+        if (dbg & 2) h->ring_epoch++;
+        else if ((rc = ring_push_and_signal(h, h->s_ring))) return rc;
         LGCA_CUDA_CHECK(cudaEventRecord(h->ev_push[slot], h->s_ring));
         h->ring_blocks++;
         n_steps -= k;

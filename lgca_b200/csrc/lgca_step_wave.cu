@@ -219,31 +219,37 @@ __global__ void __launch_bounds__(32) step_wave_kernel(const WaveArgs A, const G
     // shuffles in the row loop compile to plain SHFL without convergence bookkeeping
     const int tile = blockIdx.x;
     const int band  = tile % wp.bands;
-    int chunk = tile / wp.bands;
-    if (g.halo) {
-        // strips: the two chunks that read ghost rows are scheduled first (0 -> bottom chunk, 1 -> top chunk) so
-        // that the edge rows are finished -- and can be pushed to the neighbours -- as early as possible
-        chunk = chunk == 0 ? 0 : (chunk == 1 ? wp.chunks - 1 : chunk - 1);
-        if (A.ring_flags) {
-            // in-kernel halo wait: only tiles whose input rows [ya-K, yb+K) reach into the ghost rows depend on the
-            // neighbours' pushes (a short last chunk makes the one below it depend on them too); the rest start at once
-            const int cya = (int)g.halo + chunk * wp.chunk_rows;
-            const int cyb = min(cya + wp.chunk_rows, (int)(g.rows - g.halo));
-            const bool need_lo = cya - K < (int)g.halo, need_hi = cyb + K > (int)(g.rows - g.halo);
-            if (need_lo || need_hi) {
-                if (lane == 0) {
-                    if (need_lo) while (ld_acquire_sys(A.ring_flags + 0) < A.ring_epoch) __nanosleep(64);
-                    if (need_hi) while (ld_acquire_sys(A.ring_flags + 1) < A.ring_epoch) __nanosleep(64);
-                }
-                __syncwarp();
-            }
+    const int c    = tile / wp.bands;
+    // Row range [ya, yb) of this tile's output, relative to the first owned row.  Whole lattices: uniform chunks.
+    // Strips: tile rows 0 and 1 are the bottom and the top EDGE chunk (the only ones that read ghost rows); they are
+    // scheduled first and are shorter than the interior chunks, so that waiting for the neighbours' ghost rows at
+    // their start does not delay the end of the kernel.
+    int oa, ob;
+    const int owned = (int)(g.rows - 2 * g.halo);
+    if (wp.edge_rows == 0) {
+        oa = c * wp.chunk_rows;
+        ob = min(oa + wp.chunk_rows, owned);
+    } else if (c == 0) {
+        oa = 0; ob = wp.edge_rows;
+    } else if (c == 1) {
+        oa = owned - wp.edge_rows; ob = owned;
+    } else {
+        oa = wp.edge_rows + (c - 2) * wp.chunk_rows;
+        ob = min(oa + wp.chunk_rows, owned - wp.edge_rows);
+    }
+    if (wp.edge_rows && A.ring_flags && c < 2) {
+        // in-kernel halo wait: only the edge tiles depend on the neighbours' pushes; everyone else starts at once
+        if (lane == 0) {
+            if (c == 0) while (ld_acquire_sys(A.ring_flags + 0) < A.ring_epoch) __nanosleep(64);
+            else        while (ld_acquire_sys(A.ring_flags + 1) < A.ring_epoch) __nanosleep(64);
         }
+        __syncwarp();
     }
     const int wi    = band * WAVE_VALID - 1 + lane;          // word column of this lane (may be -1 / >= nw)
-    // output rows = the owned rows [halo, rows - halo): ghost rows of a strip are never written by the step
-    // kernel (the ring neighbours store into them), and halo is even, so ya stays even
-    const int ya    = (int)g.halo + chunk * wp.chunk_rows;                  // first output row (even)
-    const int yb    = min(ya + wp.chunk_rows, (int)(g.rows - g.halo));      // one past the last output row
+    // output rows = owned rows only: ghost rows of a strip are never written by the step kernel (the ring
+    // neighbours store into them); halo and all chunk heights are even, so ya stays even
+    const int ya    = (int)g.halo + oa;                      // first output row (even)
+    const int yb    = (int)g.halo + ob;                      // one past the last output row
     const int total = (yb - ya) + 2 * K;                     // level-0 rows to push through
     const int rows  = (int)g.rows;
 
@@ -350,7 +356,20 @@ static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
     if (e_cr && atoi(e_cr) > 0) cr = (atoi(e_cr) + 1) & ~1;
     if (cr > rows) cr = (rows + 1) & ~1;
     wp.chunk_rows = cr;
+    wp.edge_rows = 0;
     wp.chunks = (rows + cr - 1) / cr;
+    if (g.halo) {
+        // strips: two edge chunks of about 2/3 of an interior chunk (>= the rows the neighbours need and >= K + halo
+        // so that no interior chunk reads ghost rows), interior chunks in between
+        int ce = ((2 * cr / 3) + 1) & ~1;
+        const int ce_min = (int)((g.halo + (uint32_t)k + 1) & ~1u);
+        if (ce < ce_min) ce = ce_min;
+        if (2 * ce + 2 * k <= rows) {
+            wp.edge_rows = ce;
+            const int inner = rows - 2 * ce;
+            wp.chunks = 2 + (inner + cr - 1) / cr;
+        }
+    }
     wp.tiles = wp.bands * wp.chunks;
     return wp;
 }
@@ -424,6 +443,14 @@ int launch_step_wave(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, in
     case MODEL_FHP_I: return launch_m<MODEL_FHP_I>(h, in, out, k, s);
     default:          return launch_m<MODEL_FHP_II>(h, in, out, k, s);
     }
+}
+
+// true when the plan for k has edge chunks, i.e. the in-kernel ghost-row wait of the native ring is available
+bool wave_has_edge_chunks(lgca_b200_lattice* h, int k)
+{
+    if (!wave_supported(h, k)) return false;
+    if (!h->plan_valid[k] && launch_step_wave(h, nullptr, nullptr, k, 0) != 0) return false;
+    return h->plans[k].edge_rows > 0;
 }
 
 // Plans every K the handle can use and forces the kernel images to be loaded.  With CUDA's lazy module loading
