@@ -43,8 +43,12 @@ WORKLOADS = {
                  "lgca-periodic FHP-III 32768x32768 per GPU (BASELINE config C5), weak scaling in y"),
     "karman": ("FHP_III", 16384, 8192, "karman", 16,
                "lgca-karman FHP-III 16384x8192, pipe walls + cylinder, x-periodic (BASELINE config C3)"),
+    # C4 is a STRONG-scaling case: the 65536 x 32768 box is split over the N GPUs (rows per GPU = 32768 / N)
+    "box": ("FHP_II", 65536, 32768, "reflecting_back", 16,
+            "lgca-box FHP-II 65536x32768, bounce-back frame, row strips over N GPUs (BASELINE config C4), strong scaling"),
 }
-CPU_SAMPLE = {"periodic": (4096, 4096), "karman": (4096, 2048)}
+CPU_SAMPLE = {"periodic": (4096, 4096), "karman": (4096, 2048), "box": (4096, 4096)}
+STRONG = {"box"}
 
 
 def measured_peak():
@@ -168,7 +172,7 @@ def build_engine(workload, rank, world, local_rank, k_fuse):
     import lgca_b200
     from lgca_b200.ring import partition_rows
     model, dx, rows, bc, cg, _ = WORKLOADS[workload]
-    dim_y = rows * world
+    dim_y = rows if workload in STRONG else rows * world
     if world == 1:
         e = lgca_b200.Engine(model, dx, dim_y, cg_radius=cg, bf_dir="x" if workload == "karman" else 0, device=local_rank,
                              k_fuse=k_fuse, flags=lgca_b200.capi.FLAG_NO_CELL_FIELDS)
@@ -211,6 +215,9 @@ def run_b200_arm(args):
         dist.init_process_group("nccl", device_id=device)
 
     model, dx, rows, bc, cg, desc = WORKLOADS[args.workload]
+    strong = args.workload in STRONG
+    if strong:
+        rows //= world
     sites_rank = dx * rows
     sites_total = sites_rank * world
     e = build_engine(args.workload, rank, world, local_rank, args.k_fuse)
@@ -309,9 +316,9 @@ def run_b200_arm(args):
     line = None
     if rank == 0:
         line = {
-            "metric": "FHP-III site updates/s", "value": value, "unit": "site updates/s", "n_gpus": world,
+            "metric": "%s site updates/s" % model.replace("_", "-"), "value": value, "unit": "site updates/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u32 bit-planes (1 bit per site and direction)",
+            "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u32 bit-planes (1 bit per site and direction)",
             "data": "synthetic",
             "config": {"workload": desc, "global_lattice": [dx, rows * world], "sites_per_gpu": sites_rank,
                        "updates_per_step": UPDATES_PER_STEP, "k_fuse": k, "parallelism": "row strips x%d, %s" % (world, "halo ring: NCCL send/recv" if args.nccl_halo else

@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lgca_b200
 
-def run(model, dx, dy, bc, k_fuse=0, flags=0, steps=50, reps=3):
+def run(model, dx, dy, bc, k_fuse=0, flags=0, steps=48, reps=3):
     e = lgca_b200.Engine(model, dx, dy, k_fuse=k_fuse, flags=flags)
     e.apply_bc_device(bc)
     e.init_random_device(1)
@@ -25,6 +25,6 @@ if __name__ == "__main__":
             continue
         run("FHP_III", 16384, 8192, "karman", k, flags)
         run("HPP", 4096, 4096, "periodic", k, flags)
-        run("FHP_III", 32768, 32768, "periodic", k, flags, steps=10)
+        run("FHP_III", 32768, 32768, "periodic", k, flags, steps=24)
         run("FHP_II", 16384, 8192, "reflecting_back", k, flags)
-        run("FHP_I", 1400, 700, "pipe", k, flags, steps=200)
+        run("FHP_I", 1400, 700, "pipe", k, flags, steps=240)
