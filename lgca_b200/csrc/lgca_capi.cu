@@ -109,7 +109,9 @@ int lgca_b200_create(const lgca_b200_config* cfg, lgca_b200_lattice** out)
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
     h->nd  = num_dir_of(cfg->model);
-    h->k_fuse = cfg->k_fuse ? cfg->k_fuse : LGCA_MAX_K;
+    // library default: deeper fusion pays while registers last (measured on B200: HPP 6, FHP 5)
+    h->k_fuse = cfg->k_fuse ? cfg->k_fuse : (cfg->model == LGCA_B200_HPP ? 6 : 5);
+    if (cfg->model != LGCA_B200_HPP && h->k_fuse > LGCA_MAX_K_FHP) h->k_fuse = LGCA_MAX_K_FHP;
 
     const bool whole = (cfg->y_rows == 0 || cfg->y_rows == cfg->dim_y);
     if (!whole) {

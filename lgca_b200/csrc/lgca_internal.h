@@ -7,7 +7,8 @@
 #include "../../include/lgca_b200.h"
 #include "lgca_common.cuh"
 
-#define LGCA_MAX_K 4
+#define LGCA_MAX_K 8      /* HPP: up to 8 fused steps; FHP: up to LGCA_MAX_K_FHP (register budget) */
+#define LGCA_MAX_K_FHP 6
 
 namespace lgca_b200 {
 // tiling of the wavefront kernel for one k (lgca_step_wave.cu)

@@ -376,7 +376,7 @@ static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
 
 bool wave_supported(const lgca_b200_lattice* h, int k)
 {
-    if (k < 1 || k > LGCA_MAX_K) return false;
+    if (k < 1 || k > (rule_of(h->cfg.model) == MODEL_HPP ? LGCA_MAX_K : LGCA_MAX_K_FHP)) return false;
     // strips keep an even halo and start on an even row so that stored-row parity equals global parity
     if ((h->g.halo & 1u) || (h->g.y0 & 1u)) return false;
     if (h->g.rows < 8 || (int)h->g.rows < 2 * k) return false;
@@ -432,6 +432,10 @@ static int launch_m(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int
     case 2: return launch_mk<MODEL, 2>(h, in, out, s);
     case 3: return launch_mk<MODEL, 3>(h, in, out, s);
     case 4: return launch_mk<MODEL, 4>(h, in, out, s);
+    case 5: return launch_mk<MODEL, 5>(h, in, out, s);
+    case 6: return launch_mk<MODEL, 6>(h, in, out, s);
+    case 7: if (MODEL == MODEL_HPP) return launch_mk<MODEL_HPP, 7>(h, in, out, s); break;
+    case 8: if (MODEL == MODEL_HPP) return launch_mk<MODEL_HPP, 8>(h, in, out, s); break;
     }
     return set_error(LGCA_B200_EINVAL, "unsupported k_fuse %d", k);
 }

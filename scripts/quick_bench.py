@@ -3,7 +3,7 @@ import os, sys, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lgca_b200
 
-def run(model, dx, dy, bc, k_fuse=0, flags=0, steps=48, reps=3):
+def run(model, dx, dy, bc, k_fuse=0, flags=0, steps=240, reps=3):
     e = lgca_b200.Engine(model, dx, dy, k_fuse=k_fuse, flags=flags)
     e.apply_bc_device(bc)
     e.init_random_device(1)
@@ -20,11 +20,11 @@ def run(model, dx, dy, bc, k_fuse=0, flags=0, steps=48, reps=3):
 
 if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "all"
-    for flags, k in ((2, 1), (0, 1), (0, 2), (0, 3), (0, 4)):
+    for flags, k in ((2, 1), (0, 1), (0, 2), (0, 3), (0, 4), (0, 5), (0, 6), (0, 8)):
         if which != "all" and which != ("simple" if flags else f"k{k}"):
             continue
         run("FHP_III", 16384, 8192, "karman", k, flags)
         run("HPP", 4096, 4096, "periodic", k, flags)
-        run("FHP_III", 32768, 32768, "periodic", k, flags, steps=24)
+        run("FHP_III", 32768, 32768, "periodic", k, flags, steps=120)
         run("FHP_II", 16384, 8192, "reflecting_back", k, flags)
         run("FHP_I", 1400, 700, "pipe", k, flags, steps=240)

@@ -28,7 +28,8 @@ def engine_from(o, k_fuse=0, flags=0, **kw):
 
 VARIANTS = [pytest.param(dict(flags=2), id="simple"), pytest.param(dict(k_fuse=1), id="k1"),
             pytest.param(dict(k_fuse=2), id="k2"), pytest.param(dict(k_fuse=3), id="k3"),
-            pytest.param(dict(k_fuse=4), id="k4")]
+            pytest.param(dict(k_fuse=4), id="k4"), pytest.param(dict(k_fuse=6), id="k6"),
+            pytest.param(dict(), id="default")]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
