@@ -310,8 +310,11 @@ def run_b200_arm(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "step_wave_kernel<FHP_II rule, K=%d>" % k,
                 "launch_ms": kms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "dram_frac": (traffic / (kms * 1e-3) / 1e9 / peak) if traffic else None,
+                "limiter": "integer pipe (LOP3/SHF): sm__pipe_alu ~80% active in profiles/, DRAM ~50% of the copy peak",
                 "note": "algorithmic bytes = sites*(2*NUM_DIR+masks)/8 per step x k fused steps per launch; "
-                        "real DRAM traffic is ~1/k of it (temporal blocking), so frac can exceed 1"}
+                        "real DRAM traffic (`traffic`, ncu) is ~1/k of it (temporal blocking), so frac exceeds 1; "
+                        "dram_frac = traffic / launch time / peak"}
 
     line = None
     if rank == 0:
@@ -321,8 +324,10 @@ def run_b200_arm(args):
             "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "u32 bit-planes (1 bit per site and direction)",
             "data": "synthetic",
             "config": {"workload": desc, "global_lattice": [dx, rows * world], "sites_per_gpu": sites_rank,
-                       "updates_per_step": UPDATES_PER_STEP, "k_fuse": k, "parallelism": "row strips x%d, %s" % (world, "halo ring: NCCL send/recv" if args.nccl_halo else
-                                                            "halo ring: in-kernel peer stores over NVLink (CUDA IPC) + epoch flags"),
+                       "updates_per_step": UPDATES_PER_STEP, "k_fuse": k, "parallelism": "single GPU" if world == 1 else "row strips x%d, %s" % (
+                           world, "halo ring: NCCL send/recv" if args.nccl_halo else
+                           "halo ring: peer stores into the neighbours' ghost rows over NVLink (CUDA IPC) + device epoch flags, "
+                           "edge tiles wait in-kernel"),
                        "cache": "inputs larger than L2 (%.0f MB of bit-planes per GPU vs 126 MB L2)" % (
                            sites_rank * info.num_planes / 8 / 1e6) if sites_rank * info.num_planes / 8 > 200e6 else
                        "lattice (%.0f MB) is L2-resident" % (sites_rank * info.num_planes / 8 / 1e6),

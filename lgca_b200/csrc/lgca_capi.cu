@@ -321,6 +321,12 @@ int lgca_b200_snapshot(lgca_b200_lattice* h)
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     // do not overwrite the snapshot while the post stream still reads it
     LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_post, 0));
+    // native ring: the ghost rows of the live buffer are written by the neighbours; the coarse means of the top
+    // coarse row read one of them, so the snapshot waits for the current epoch to have arrived
+    if (h->ring_connected && h->ring_epoch) {
+        int rc = ring_wait_current_epoch(h);
+        if (rc) return rc;
+    }
     LGCA_CUDA_CHECK(cudaMemcpyAsync(h->snap, h->planes[h->cur], plane_words(h) * sizeof(uint32_t) * h->nd,
                                     cudaMemcpyDeviceToDevice, h->s_compute));
     LGCA_CUDA_CHECK(cudaEventRecord(h->ev_snap, h->s_compute));

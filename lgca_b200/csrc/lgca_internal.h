@@ -80,6 +80,7 @@ bool wave_supported(const lgca_b200_lattice* h, int k);
 int wave_prepare(lgca_b200_lattice* h);
 bool wave_has_edge_chunks(lgca_b200_lattice* h, int k);
 int simple_prepare(lgca_b200_lattice* h);
+int ring_wait_current_epoch(lgca_b200_lattice* h); // lgca_ring.cu: stream-ordered wait for the neighbours' latest pushes
 
 // lgca_pack.cu : reference layouts <-> bit-planes
 int launch_pack_state(lgca_b200_lattice* h, const uint8_t* d_bytes, uint32_t* planes, uint32_t row0, uint32_t nrows,

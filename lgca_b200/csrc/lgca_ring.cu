@@ -89,6 +89,14 @@ static int ring_push_and_signal(lgca_b200_lattice* h, cudaStream_t s)
     return 0;
 }
 
+int ring_wait_current_epoch(lgca_b200_lattice* h)
+{
+    ring_wait_kernel<<<1, 2, 0, h->s_compute>>>((volatile uint32_t*)h->ring_flags, h->ring_epoch);
+    h->launches++;
+    LGCA_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
 static int open_peer(const RingBlob& blob, int my_device, void* planes[2], void** flags)
 {
     if (blob.magic != RING_MAGIC) return set_error(LGCA_B200_EINVAL, "not a ring descriptor");
