@@ -185,11 +185,60 @@ def build_engine(workload, rank, world, local_rank, k_fuse):
     return e
 
 
-def bench_step(ring, e, coarse_out):
-    """One bench step with the lattice resident in HBM: 100 updates + coarse post-process + read-back."""
-    ring.step(UPDATES_PER_STEP)
+class VtiWriter(threading.Thread):
+    """Writes the coarse fields of every bench step as `mean_res_<step>_r<rank>.vti` in the background (config C5:
+    "coarse-grained .vti output every 100 steps"); double-buffered so that the write of step i overlaps step i+1."""
+
+    def __init__(self, directory, rank, cdx, cdy, origin_y):
+        super().__init__(daemon=True)
+        import queue
+        self.q, self.dir, self.rank, self.cdx, self.cdy, self.oy = queue.Queue(maxsize=1), directory, rank, cdx, cdy, origin_y
+        self.bytes = 0
+        self.files = 0
+        self.error = None
+        self.start()
+
+    def run(self):
+        from lgca_b200.vti import write_mean_vti
+        while True:
+            item = self.q.get()
+            if item is None:
+                self.q.task_done()
+                return
+            step, fields = item
+            try:
+                path = os.path.join(self.dir, "mean_res_%d_r%d.vti" % (step, self.rank))
+                write_mean_vti(path, self.cdx, self.cdy, fields["mean_density"], fields["mean_momentum"], self.oy)
+                self.bytes += os.path.getsize(path)
+                self.files += 1
+                os.unlink(path)  # the benchmark keeps no output
+            except Exception as ex:  # never leave the main thread waiting on a dead writer
+                self.error = repr(ex)
+            finally:
+                self.q.task_done()
+
+    def submit(self, step, fields):
+        self.q.put((step, fields))  # blocks while the previous file is still being written
+
+    def drain(self):
+        self.q.join()
+
+
+def bench_step(ring, e, coarse_bufs, writer, step_no):
+    """One bench step with the lattice resident in HBM: 100 updates + snapshot + coarse post-process + read-back of
+    the coarse fields + (asynchronous) .vti write."""
+    ring.step(UPDATES_PER_STEP)        # asynchronous: the GPU works while the previous file is being written
     e.snapshot()
-    e.post_process(cell=False, mean=True, exact=False, out=coarse_out)
+    out = coarse_bufs[0]
+    if writer is not None:
+        writer.drain()                 # the previous step's file is done before its buffer is refilled
+    e.post_process(cell=False, mean=True, exact=False, out=out)
+    if writer is not None:
+        writer.submit(step_no * UPDATES_PER_STEP, out)
+
+
+def info_y_begin(e):
+    return int(e.info().y_begin)
 
 
 def run_b200_arm(args):
@@ -225,7 +274,11 @@ def run_b200_arm(args):
     ring.start()
     info = e.info()
     particles0 = e.count_particles()
-    coarse = {}
+    coarse_bufs = [{}, {}]
+    coarse = coarse_bufs[0]
+    import tempfile
+    vti_dir = tempfile.mkdtemp(prefix="lgca_vti_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    writer = None if args.no_vti else VtiWriter(vti_dir, rank, dx // (2 * cg), rows // (2 * cg), info_y_begin(e) // (2 * cg))
 
     def barrier():
         e.sync()
@@ -234,8 +287,12 @@ def run_b200_arm(args):
             dist.barrier()
 
     # ---- device-resident throughput ----------------------------------------------------------------
+    step_no = 0
     for _ in range(max(args.warmup, 3)):
-        bench_step(ring, e, coarse)
+        step_no += 1
+        bench_step(ring, e, coarse_bufs, writer, step_no)
+    if writer:
+        writer.drain()
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -244,7 +301,10 @@ def run_b200_arm(args):
     launches0 = e.launch_count()
     ev0.record(stream)
     for _ in range(args.steps):
-        bench_step(ring, e, coarse)
+        step_no += 1
+        bench_step(ring, e, coarse_bufs, writer, step_no)
+    if writer:
+        writer.drain()  # the last file is on disk before the clock stops
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
@@ -271,8 +331,14 @@ def run_b200_arm(args):
             ring.start()                             # ghost rows of the freshly uploaded strips
         ring.step(UPDATES_PER_STEP)                  # 100 x collide_and_propagate()
         e.snapshot()                                 # copy_data_to_output_buffer()
+        if writer:
+            writer.drain()
         e.post_process(cell=False, mean=True, exact=False, out=coarse)  # post_process() -> host coarse fields
+        if writer:
+            writer.submit(0, coarse)                 # IoVti::write of the coarse fields
         e.download(host_state.array)                 # copy_data_from_device()
+    if writer:
+        writer.drain()
     barrier()
     e2e_s = time.perf_counter() - t0
     if world > 1:
@@ -308,7 +374,7 @@ def run_b200_arm(args):
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "step_wave_kernel<FHP_II rule, K=%d>" % k,
+                "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "kernel": "step_wave_kernel<FHP_II rule, K=%d>" % k,
                 "launch_ms": kms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "dram_frac": (traffic / (kms * 1e-3) / 1e9 / peak) if traffic else None,
                 "limiter": "integer pipe (LOP3/SHF): sm__pipe_alu ~80% active in profiles/, DRAM ~50% of the copy peak",
@@ -331,7 +397,9 @@ def run_b200_arm(args):
                        "cache": "inputs larger than L2 (%.0f MB of bit-planes per GPU vs 126 MB L2)" % (
                            sites_rank * info.num_planes / 8 / 1e6) if sites_rank * info.num_planes / 8 > 200e6 else
                        "lattice (%.0f MB) is L2-resident" % (sites_rank * info.num_planes / 8 / 1e6),
-                       "step": "100 updates + snapshot + coarse post-process + D2H of coarse fields"},
+                       "step": "100 updates + snapshot + coarse post-process + D2H of coarse fields + .vti write of them "
+                               "(%s)" % ("disabled" if args.no_vti else "%d files, %.1f MB each, background thread" % (
+                                   writer.files, writer.bytes / max(writer.files, 1) / 1e6))},
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "site updates/s", "h2d_bytes_per_step": sites_rank * world,
                     "d2h_bytes_per_step": (sites_rank + coarse_bytes) * world, "steps": e2e_steps,
@@ -352,6 +420,14 @@ def run_b200_arm(args):
         if args.workload == "periodic" and not args.no_karman:
             e.close()
             line["karman"] = karman_extra(args, peak)
+    if writer:
+        writer.q.put(None)
+        if writer.error:
+            raise SystemExit("bench.py: .vti writer failed: %s" % writer.error)
+    try:
+        os.rmdir(vti_dir)
+    except OSError:
+        pass
     if line is not None:
         print(json.dumps(line))
     e.close()
@@ -387,6 +463,7 @@ def main():
     ap.add_argument("--cpu-updates", type=int, default=12, help="updates of the bounded CPU sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-karman", action="store_true")
+    ap.add_argument("--no-vti", action="store_true", help="skip the .vti write of the coarse fields")
     ap.add_argument("--nccl-halo", action="store_true", help="move ghost rows with NCCL send/recv instead of the native peer-store ring")
     args = ap.parse_args()
     if args.impl == "reference":

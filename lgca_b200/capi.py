@@ -201,7 +201,7 @@ class Engine:
         self._check(self.L.lgca_b200_snapshot(self.h))
 
     def post_process(self, cell=True, mean=True, exact=True, out=None):
-        out = out or {}
+        out = {} if out is None else out
         n = self.cells
         if cell:
             out.setdefault("cell_density", np.empty(n, np.float32))

@@ -232,3 +232,38 @@ def test_device_init_and_conservation():
     assert np.array_equal(e.download(), e2.download())
     e.close()
     e2.close()
+
+
+def test_two_host_threads_step_and_post_process():
+    """The reference's viewers drive one lattice from two host threads (apps/pipe/pipe_viewer.cpp:105,150):
+    stepping + snapshot on one, post_process on the other.  The snapshot must insulate the two."""
+    import threading
+    import lgca_b200
+    o = Oracle("FHP_III", "karman", 10, 0.2, 16)
+    o.apply_bc("karman")
+    o.init("random")
+    e = engine_from(o)
+    n0 = e.count_particles()
+    errors, densities = [], []
+    e.snapshot()
+
+    def poster():
+        try:
+            for _ in range(30):
+                f = e.post_process(cell=True, mean=True, exact=True)
+                densities.append(float(f["cell_density"].sum()))
+        except Exception as ex:  # pragma: no cover
+            errors.append(ex)
+
+    t = threading.Thread(target=poster)
+    t.start()
+    for _ in range(30):
+        e.step(5)
+        e.snapshot()
+    t.join()
+    assert not errors
+    # every post-processed snapshot is a consistent state: its per-cell density sums to the particle count
+    assert all(abs(d - n0) < 0.5 for d in densities), (n0, densities[:5])
+    o.step(150)
+    assert np.array_equal(e.download(), o.state)
+    e.close()
