@@ -225,16 +225,21 @@ class VtiWriter(threading.Thread):
 
 
 def bench_step(ring, e, coarse_bufs, writer, step_no):
-    """One bench step with the lattice resident in HBM: 100 updates + snapshot + coarse post-process + read-back of
-    the coarse fields + (asynchronous) .vti write."""
-    ring.step(UPDATES_PER_STEP)        # asynchronous: the GPU works while the previous file is being written
-    e.snapshot()
+    """One bench step with the lattice resident in HBM: 100 updates + snapshot + coarse post-process of a snapshot +
+    read-back of the coarse fields + .vti write.
+
+    Software-pipelined like the reference's viewers, which simulate and post-process concurrently
+    (apps/pipe/pipe_viewer.cpp:100-184): the 100 updates of this step are enqueued first, then the host post-processes
+    the PREVIOUS snapshot (device snapshot buffer insulates it) while the GPU keeps stepping, then the new state is
+    snapshotted.  Every step performs exactly one of each operation."""
+    ring.step(UPDATES_PER_STEP)        # asynchronous
     out = coarse_bufs[0]
     if writer is not None:
-        writer.drain()                 # the previous step's file is done before its buffer is refilled
-    e.post_process(cell=False, mean=True, exact=False, out=out)
+        writer.drain()                 # the previous file is done before its buffer is refilled
+    e.post_process(cell=False, mean=True, exact=False, out=out)   # of the snapshot taken at the end of the previous step
     if writer is not None:
         writer.submit(step_no * UPDATES_PER_STEP, out)
+    e.snapshot()                       # stream-ordered after the 100 updates (and after the post-process read)
 
 
 def info_y_begin(e):
@@ -288,6 +293,7 @@ def run_b200_arm(args):
 
     # ---- device-resident throughput ----------------------------------------------------------------
     step_no = 0
+    e.snapshot()
     for _ in range(max(args.warmup, 3)):
         step_no += 1
         bench_step(ring, e, coarse_bufs, writer, step_no)
