@@ -57,6 +57,17 @@ static int ensure_stage(lgca_b200_lattice* h)
     return 0;
 }
 
+static int ensure_copy_stream(lgca_b200_lattice* h)
+{
+    if (h->s_copy) return 0;
+    LGCA_CUDA_CHECK(cudaStreamCreateWithFlags(&h->s_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        LGCA_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_stage_free[i], cudaEventDisableTiming));
+        LGCA_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_stage_full[i], cudaEventDisableTiming));
+    }
+    return 0;
+}
+
 static inline uint32_t own_rows(const lgca_b200_lattice* h) { return h->g.rows - 2 * h->g.halo; }
 static inline size_t plane_words(const lgca_b200_lattice* h) { return (size_t)h->g.plane_stride; }
 
@@ -185,6 +196,7 @@ int lgca_b200_destroy(lgca_b200_lattice* h)
     if (h->h_draw_bytes) cudaFreeHost(h->h_draw_bytes);
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_post) cudaStreamDestroy(h->s_post);
+    if (h->s_copy) cudaStreamDestroy(h->s_copy);
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
     if (h->ev_post) cudaEventDestroy(h->ev_post);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
@@ -251,12 +263,22 @@ int lgca_b200_upload(lgca_b200_lattice* h, const uint8_t* state, const int32_t* 
         h->have_rnd = 1;
     }
     if (state) {
+        // two-stage pipeline over the staging buffers: the copy engine (s_copy) moves chunk c+1 over PCIe while the
+        // SMs (compute stream) transpose chunk c into bit-planes
+        if ((rc = ensure_copy_stream(h))) return rc;
         const uint32_t rpc = (uint32_t)std::max<size_t>(1, h->stage_bytes / g.dim_x);
+        LGCA_CUDA_CHECK(cudaEventRecord(h->ev_stage_free[0], s)); // staging buffers are free once earlier work is done
+        LGCA_CUDA_CHECK(cudaEventRecord(h->ev_stage_free[1], s));
+        buf = 0;
         for (uint32_t r0 = 0; r0 < own; r0 += rpc, buf ^= 1) {
             const uint32_t nr = std::min(rpc, own - r0);
+            LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_copy, h->ev_stage_free[buf], 0));
             LGCA_CUDA_CHECK(cudaMemcpyAsync(h->d_stage[buf], state + (size_t)r0 * g.dim_x, (size_t)nr * g.dim_x,
-                                            cudaMemcpyHostToDevice, s));
+                                            cudaMemcpyHostToDevice, h->s_copy));
+            LGCA_CUDA_CHECK(cudaEventRecord(h->ev_stage_full[buf], h->s_copy));
+            LGCA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_stage_full[buf], 0));
             if ((rc = launch_pack_state(h, (const uint8_t*)h->d_stage[buf], h->planes[h->cur], g.halo + r0, nr, s))) return rc;
+            LGCA_CUDA_CHECK(cudaEventRecord(h->ev_stage_free[buf], s));
         }
         h->have_state = 1;
     }
@@ -274,14 +296,23 @@ int lgca_b200_download(lgca_b200_lattice* h, uint8_t* state)
     const uint32_t own = own_rows(h);
     cudaStream_t s = h->s_compute;
     const uint32_t rpc = (uint32_t)std::max<size_t>(1, h->stage_bytes / g.dim_x);
+    // two-stage pipeline: the SMs unpack chunk c+1 while the copy engine sends chunk c over PCIe
+    if ((rc = ensure_copy_stream(h))) return rc;
+    LGCA_CUDA_CHECK(cudaEventRecord(h->ev_stage_free[0], h->s_copy));
+    LGCA_CUDA_CHECK(cudaEventRecord(h->ev_stage_free[1], h->s_copy));
     int buf = 0;
     for (uint32_t r0 = 0; r0 < own; r0 += rpc, buf ^= 1) {
         const uint32_t nr = std::min(rpc, own - r0);
+        LGCA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_stage_free[buf], 0));
         if ((rc = launch_unpack_state(h, h->planes[h->cur], (uint8_t*)h->d_stage[buf], g.halo + r0, nr, s))) return rc;
+        LGCA_CUDA_CHECK(cudaEventRecord(h->ev_stage_full[buf], s));
+        LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_copy, h->ev_stage_full[buf], 0));
         LGCA_CUDA_CHECK(cudaMemcpyAsync(state + (size_t)r0 * g.dim_x, h->d_stage[buf], (size_t)nr * g.dim_x,
-                                        cudaMemcpyDeviceToHost, s));
+                                        cudaMemcpyDeviceToHost, h->s_copy));
+        LGCA_CUDA_CHECK(cudaEventRecord(h->ev_stage_free[buf], h->s_copy));
     }
     LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
+    LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_copy));
     return 0;
 }
 

@@ -37,6 +37,8 @@ struct lgca_b200_lattice {
     int              has_ns, has_sl;
     int              have_state, have_types, have_rnd;
     cudaStream_t     s_compute, s_post;
+    cudaStream_t     s_copy;                 // PCIe copies of upload/download, pipelined against pack/unpack
+    cudaEvent_t      ev_stage_free[2], ev_stage_full[2];
     cudaEvent_t      ev_snap, ev_post, ev_t0, ev_t1;
     // staging (lazily allocated, reused)
     void*            d_stage[2];
