@@ -16,7 +16,7 @@
 // the movers of the two triangles (even / odd directions) are counted with one full adder each, which
 // classifies every site (one mover, head-on candidate, 120-degree pair, alternating triple) in a few ops;
 // the rest-particle rules of FHP-II collapse to "flip a trio of adjacent directions and the rest bit".
-// About 40 LOP3 per 32 sites for FHP-II/III (the reference's formulas lifted verbatim need 76).
+// 36 LOP3 per 32 sites for FHP-II/III (the reference's formulas lifted verbatim compile to 76).
 #pragma once
 #include <stdint.h>
 
@@ -83,17 +83,20 @@ LGCA_HD void collide_hpp(uint32_t (&n)[7])
 //   FHP-II: rest + single mover c             -> movers c-1,c+1 (rest consumed)
 //           movers c-1,c+1 only, no rest      -> mover c + rest
 //
-// Network (change-mask form, out = in ^ ch).  The six movers are counted per TRIANGLE -- even
-// directions (0,2,4) and odd directions (1,3,5) -- with one full adder each:
+// Network.  The six movers are counted per TRIANGLE -- even directions (0,2,4) and odd directions (1,3,5) --
+// with one full adder each:
 //     s_e,c_e = XOR3/MAJ(n0,n2,n4)     s_o,c_o = XOR3/MAJ(n1,n3,n5)
 // which classifies every site with a handful of 3-input ops:
-//     exactly one mover            one = (s_e^s_o) & ~(c_e|c_o)
 //     one even + one odd mover     g1  = s_e & s_o & ~(c_e|c_o)      (adjacent or head-on pair)
-//     two movers of one triangle   d2  = ~s_e & ~s_o & (c_e^c_o)     (always 120 degrees apart)
 //     alternating triple           tri = (s_e^s_o) & (c_e^c_o) & ~(s_e^c_e)
-// Head-on pairs are g1 & n_j & n_{j+3}.  Both rest rules flip the trio {c-1,c,c+1} and the rest bit
-// around a centre c, and fire exactly when  E = r ? one : d2 ; direction i then flips iff
-// E & (n_i | (r ? n_{i-1}|n_{i+1} : n_{i-1}&n_{i+1})).
+// Head-on pairs are g1 & n_j & n_{j+3}; pair (j, j+3) flips with T_j = tri | h_j | (p ? h_{j+1} : h_{j+2}).
+// Rest rules (FHP-II/III).  Both fire only when ONE triangle is empty: "rest + single mover c" (the other
+// triangle holds exactly one mover) and "movers c-1, c+1, no rest" (the other triangle holds exactly two).
+// In both, the occupied triangle is cleared of what it holds, and every vertex v of the EMPTY triangle is set
+// unless the vertex opposite to it (v+3, in the occupied triangle) is occupied.  Hence, with
+//     EE = even triangle empty & (r ? odd has one : odd has two),   EO = likewise with the roles swapped,
+// direction i of the even triangle becomes   EE ? ~n_{i+3} : (~EO & (n_i ^ T_i))   and symmetrically for odd i;
+// the rest bit flips when EE | EO.  36 LOP3 in total for FHP-II/III, 25 for FHP-I (counted in the SASS).
 // ---------------------------------------------------------------------------------------------
 template <bool WITH_REST>
 LGCA_HD void collide_fhp(uint32_t (&n)[7], uint32_t p)
@@ -117,22 +120,25 @@ LGCA_HD void collide_fhp(uint32_t (&n)[7], uint32_t p)
     const uint32_t t30 = lop3<LUT_OR3>(tri, h3, lop3<LUT_MUX>(p, h1, h2));
 
     if (WITH_REST) {
-        const uint32_t r   = n[6];
-        const uint32_t one = lop3<TA & ~TB>(sx, cor, 0u);          // exactly one mover
-        const uint32_t d2  = lop3<~TA & ~TB & TC & 0xFF>(se, so, cxr); // two movers 120 degrees apart
-        const uint32_t E   = lop3<LUT_MUX>(r, one, d2);           // a rest rule fires (== change of the rest bit)
+        const uint32_t r  = n[6];
+        // fo: the odd triangle holds exactly one mover (r set) or exactly two (r clear); fe likewise for the even one
+        constexpr uint32_t LUT_F = (TA & TB & ~TC) | (~TA & ~TB & TC & 0xFF); // a ? (b & ~c) : (~b & c)
+        const uint32_t fo = lop3<LUT_F>(r, so, co);
+        const uint32_t fe = lop3<LUT_F>(r, se, ce);
+        const uint32_t EE = lop3<TA & ~TB & ~TC & 0xFF>(fo, se, ce); // even triangle empty, odd one triggers a rest rule
+        const uint32_t EO = lop3<TA & ~TB & ~TC & 0xFF>(fe, so, co);
         uint32_t o[6];
 #pragma unroll
         for (int i = 0; i < 6; ++i) {
-            // y = r ? (n_{i-1} | n_{i+1}) : (n_{i-1} & n_{i+1})
-            const uint32_t y = lop3<(TA & (TB | TC)) | (~TA & TB & TC & 0xFF)>(r, n[(i + 5) % 6], n[(i + 1) % 6]);
-            const uint32_t R = lop3<TA & (TB | TC)>(E, n[i], y);
-            const uint32_t T = (i == 1 || i == 4) ? t14 : ((i == 2 || i == 5) ? t25 : t30);
-            o[i] = lop3<LUT_XOR_OR>(n[i], T, R);
+            const uint32_t T    = (i == 1 || i == 4) ? t14 : ((i == 2 || i == 5) ? t25 : t30);
+            const uint32_t own  = (i & 1) ? EO : EE;   // this direction's triangle is the empty one
+            const uint32_t oth  = (i & 1) ? EE : EO;   // ... or the one being cleared
+            const uint32_t w    = lop3<~TA & (TB ^ TC) & 0xFF>(oth, n[i], T);         // ~oth & (n_i ^ T)
+            o[i] = lop3<(TA & ~TB) | (~TA & TC)>(own, n[(i + 3) % 6], w);             // own ? ~n_{i+3} : w
         }
 #pragma unroll
         for (int i = 0; i < 6; ++i) n[i] = o[i];
-        n[6] = r ^ E;
+        n[6] = lop3<TA ^ (TB | TC)>(r, EE, EO);
     } else {
         n[1] ^= t14; n[4] ^= t14;
         n[2] ^= t25; n[5] ^= t25;
