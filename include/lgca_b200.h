@@ -127,6 +127,16 @@ int  lgca_b200_mean_velocity(lgca_b200_lattice* h, float out[2]);
 int  lgca_b200_body_force(lgca_b200_lattice* h, int forcing, const int32_t* draws, size_t n_draws,
                           size_t* consumed, uint32_t* reverted);
 
+/* The three stages of the body force as separate calls, for drivers that own several strips (multi-GPU): gather the
+ * bytes of the drawn cells on every strip (bit 7 set = not an eligible FLUID cell of this strip), combine them
+ * (element-wise minimum over strips), replay the batch in draw order on the host (pure host function, no GPU), apply
+ * the changed cells on every strip (cells outside a strip are ignored there). */
+int  lgca_b200_body_force_gather(lgca_b200_lattice* h, const int32_t* cells, size_t n, uint8_t* bytes_out);
+int  lgca_b200_body_force_replay(int model, int bf_dir, int forcing, const int32_t* cells, const uint8_t* bytes, size_t n,
+                                 size_t* consumed, uint32_t* reverted, int32_t* changed_cells, uint8_t* changed_bytes,
+                                 size_t* n_changed);
+int  lgca_b200_body_force_apply(lgca_b200_lattice* h, const int32_t* cells, const uint8_t* new_bytes, size_t n);
+
 /* ---- Lattice::get_n_particles(), src/lattice.h:165 / src/lattice.cpp:180-195 ---- (live state) */
 int  lgca_b200_count_particles(lgca_b200_lattice* h, uint64_t* out);
 

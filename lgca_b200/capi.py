@@ -17,7 +17,8 @@ SYMBOLS = [
     "lgca_b200_create", "lgca_b200_destroy", "lgca_b200_last_error", "lgca_b200_version",
     "lgca_b200_device_count", "lgca_b200_host_alloc", "lgca_b200_host_free", "lgca_b200_upload",
     "lgca_b200_download", "lgca_b200_step", "lgca_b200_snapshot", "lgca_b200_post_process",
-    "lgca_b200_mean_velocity", "lgca_b200_body_force", "lgca_b200_count_particles",
+    "lgca_b200_mean_velocity", "lgca_b200_body_force", "lgca_b200_body_force_gather", "lgca_b200_body_force_replay",
+    "lgca_b200_body_force_apply", "lgca_b200_count_particles",
     "lgca_b200_init_random_device", "lgca_b200_apply_bc_device", "lgca_b200_sync",
     "lgca_b200_compute_stream", "lgca_b200_timed_steps", "lgca_b200_timed_kernel", "lgca_b200_launch_count", "lgca_b200_get_info",
     "lgca_b200_halo_rows", "lgca_b200_halo_bytes", "lgca_b200_halo_export", "lgca_b200_halo_import",
@@ -75,6 +76,10 @@ def load_library():
     L.lgca_b200_post_process.argtypes = [vp, vp, vp, vp, vp, i32]
     L.lgca_b200_mean_velocity.argtypes = [vp, vp]
     L.lgca_b200_body_force.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
+    L.lgca_b200_body_force_gather.argtypes = [vp, vp, C.c_size_t, vp]
+    L.lgca_b200_body_force_replay.argtypes = [i32, i32, i32, vp, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32),
+                                              vp, vp, C.POINTER(C.c_size_t)]
+    L.lgca_b200_body_force_apply.argtypes = [vp, vp, vp, C.c_size_t]
     L.lgca_b200_count_particles.argtypes = [vp, C.POINTER(u64)]
     L.lgca_b200_init_random_device.argtypes = [vp, u64]
     L.lgca_b200_apply_bc_device.argtypes = [vp, C.c_char_p]
@@ -103,6 +108,24 @@ def load_library():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def body_force_replay(model, bf_dir, forcing, cells, cell_bytes):
+    """Host-only ordered replay of one batch of body-force draws (see lgca_b200_body_force_replay)."""
+    L = load_library()
+    model = MODELS[model] if isinstance(model, str) else int(model)
+    if isinstance(bf_dir, (bytes, str)):
+        bf_dir = ord(bf_dir) if len(bf_dir) and bf_dir not in (b"\0", "\0") else 0
+    cells = np.ascontiguousarray(cells, np.int32)
+    cell_bytes = np.ascontiguousarray(cell_bytes, np.uint8)
+    n = cells.size
+    ch_cells, ch_bytes = np.empty(max(n, 1), np.int32), np.empty(max(n, 1), np.uint8)
+    used, rev, nch = C.c_size_t(0), C.c_uint32(0), C.c_size_t(0)
+    rc = L.lgca_b200_body_force_replay(model, bf_dir, int(forcing), _ptr(cells), _ptr(cell_bytes), n, C.byref(used), C.byref(rev),
+                                       _ptr(ch_cells), _ptr(ch_bytes), C.byref(nch))
+    if rc != 0:
+        raise LgcaError(L.lgca_b200_last_error().decode())
+    return int(used.value), int(rev.value), ch_cells[: nch.value].copy(), ch_bytes[: nch.value].copy()
 
 
 class PinnedArray:
@@ -225,6 +248,17 @@ class Engine:
         used, rev = C.c_size_t(0), C.c_uint32(0)
         self._check(self.L.lgca_b200_body_force(self.h, int(forcing), _ptr(draws), draws.size, C.byref(used), C.byref(rev)))
         return int(used.value), int(rev.value)
+
+    def body_force_gather(self, cells):
+        cells = np.ascontiguousarray(cells, np.int32)
+        out = np.empty(cells.size, np.uint8)
+        self._check(self.L.lgca_b200_body_force_gather(self.h, _ptr(cells), cells.size, _ptr(out)))
+        return out
+
+    def body_force_apply(self, cells, new_bytes):
+        cells = np.ascontiguousarray(cells, np.int32)
+        new_bytes = np.ascontiguousarray(new_bytes, np.uint8)
+        self._check(self.L.lgca_b200_body_force_apply(self.h, _ptr(cells), _ptr(new_bytes), cells.size))
 
     def count_particles(self):
         v = C.c_uint64(0)

@@ -438,86 +438,143 @@ int lgca_b200_count_particles(lgca_b200_lattice* h, uint64_t* out)
     return 0;
 }
 
-// Exact body force (src/omp_lattice.cpp:254-346): the sequential semantics of the reference are kept
-// by letting the device gather the byte states of a batch of drawn cells, replaying the draws in
-// order on the host against those bytes (a cell changed by an earlier draw of the same call is
-// tracked in a small map), and scattering the changed cells back.
+// Exact body force (src/omp_lattice.cpp:254-346).  The reference is sequential: draw a cell, flip it if it is an
+// eligible FLUID cell, stop after `forcing` flips.  Here the device GATHERs the byte states of a batch of drawn cells,
+// the draws are REPLAYed in order on the host against those bytes (a cell changed by an earlier draw of the same
+// batch is tracked), and the changed cells are APPLIED back.  The three stages are separate entry points so that a
+// multi-GPU driver can combine the gathered bytes of all strips before the replay.
+
+static int ensure_draw_buffers(lgca_b200_lattice* h, size_t n)
+{
+    if (n <= h->draw_cap) return 0;
+    cudaFree(h->d_draws); cudaFree(h->d_draw_bytes);
+    if (h->h_draw_bytes) cudaFreeHost(h->h_draw_bytes);
+    h->d_draws = nullptr; h->d_draw_bytes = nullptr; h->h_draw_bytes = nullptr;
+    h->draw_cap = 0;
+    const size_t cap = std::max<size_t>(n, 1 << 16);
+    // d_draws doubles as the scatter buffer: cap int32 cells followed by cap bytes
+    LGCA_CUDA_CHECK(cudaMalloc((void**)&h->d_draws, cap * 5 + 16));
+    LGCA_CUDA_CHECK(cudaMalloc((void**)&h->d_draw_bytes, cap));
+    LGCA_CUDA_CHECK(cudaHostAlloc((void**)&h->h_draw_bytes, cap, cudaHostAllocDefault));
+    h->draw_cap = cap;
+    return 0;
+}
+
+int lgca_b200_body_force_gather(lgca_b200_lattice* h, const int32_t* cells, size_t n, uint8_t* bytes_out)
+{
+    if (!h || (n && (!cells || !bytes_out))) return set_error(LGCA_B200_EINVAL, "null argument");
+    if (n == 0) return 0;
+    LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+    int rc = ensure_draw_buffers(h, n);
+    if (rc) return rc;
+    cudaStream_t s = h->s_compute;
+    LGCA_CUDA_CHECK(cudaMemcpyAsync(h->d_draws, cells, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    if ((rc = launch_gather_cells(h, h->planes[h->cur], h->d_draws, n, h->d_draw_bytes, s))) return rc;
+    LGCA_CUDA_CHECK(cudaMemcpyAsync(h->h_draw_bytes, h->d_draw_bytes, n, cudaMemcpyDeviceToHost, s));
+    LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
+    memcpy(bytes_out, h->h_draw_bytes, n);
+    return 0;
+}
+
+int lgca_b200_body_force_apply(lgca_b200_lattice* h, const int32_t* cells, const uint8_t* new_bytes, size_t n)
+{
+    if (!h || (n && (!cells || !new_bytes))) return set_error(LGCA_B200_EINVAL, "null argument");
+    if (n == 0) return 0;
+    LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+    int rc = ensure_draw_buffers(h, n);
+    if (rc) return rc;
+    cudaStream_t s = h->s_compute;
+    std::vector<uint8_t> blob(n * 5);
+    memcpy(blob.data(), cells, n * 4);
+    memcpy(blob.data() + n * 4, new_bytes, n);
+    LGCA_CUDA_CHECK(cudaMemcpyAsync(h->d_draws, blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
+    if ((rc = launch_apply_flips(h, h->planes[h->cur], h->d_draws, n, s))) return rc;
+    LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
+    return 0;
+}
+
+// Host-only (no GPU): ordered replay of one batch.  bytes[i] = state byte of cells[i] with bit 7 set when the cell
+// is not an eligible FLUID cell.  Stops after the draw that brings the reverted count to `forcing` (do-while of the
+// reference: at least one draw is consumed even for forcing <= 0).  changed_* receive each changed cell once.
+int lgca_b200_body_force_replay(int model, int bf_dir, int forcing, const int32_t* cells, const uint8_t* bytes, size_t n,
+                                size_t* consumed, uint32_t* reverted, int32_t* changed_cells, uint8_t* changed_bytes,
+                                size_t* n_changed)
+{
+    if ((n && (!cells || !bytes || !changed_cells || !changed_bytes)) || !consumed || !reverted || !n_changed)
+        return set_error(LGCA_B200_EINVAL, "null argument");
+    std::unordered_map<int32_t, uint8_t> touched;
+    std::vector<int32_t> order; // first-touch order keeps the output deterministic
+    size_t pos = 0;
+    uint32_t rev = 0;
+    const char bf = (char)bf_dir;
+    bool done = false;
+    while (pos < n && !done) {
+        const int32_t cell = cells[pos];
+        uint8_t b = bytes[pos];
+        ++pos;
+        if (!(b & 0x80)) {
+            auto it = touched.find(cell);
+            if (it != touched.end()) b = it->second;
+            uint8_t w = b;
+            if (model == LGCA_B200_HPP) { // src/omp_lattice.cpp:295-310
+                if (bf == 'x' && !(b & 1) && (b & 4)) { w = (uint8_t)((w | 1) & ~4); ++rev; }
+                else if (bf == 'y' && (b & 2) && !(b & 8)) { w = (uint8_t)((w | 8) & ~2); ++rev; }
+            } else {                      // src/omp_lattice.cpp:313-338
+                if (bf == 'x' && !(b & 1) && (b & 8)) { w = (uint8_t)((w | 1) & ~8); ++rev; }
+                else if (bf == 'y') {
+                    if ((b & 2) && !(b & 32)) { w = (uint8_t)((w | 32) & ~2); ++rev; }
+                    if ((b & 4) && !(b & 16)) { w = (uint8_t)((w | 16) & ~4); ++rev; }
+                }
+            }
+            if (w != b) {
+                if (it == touched.end()) order.push_back(cell);
+                touched[cell] = w;
+            }
+        }
+        if (!((int64_t)rev < (int64_t)forcing)) done = true; // do { ... } while (reverted < forcing && ...)
+    }
+    size_t k = 0;
+    for (int32_t c : order) { changed_cells[k] = c; changed_bytes[k] = touched[c]; ++k; }
+    *consumed = pos;
+    *reverted = rev;
+    *n_changed = k;
+    return 0;
+}
+
 int lgca_b200_body_force(lgca_b200_lattice* h, int forcing, const int32_t* draws, size_t n_draws, size_t* consumed,
                          uint32_t* reverted)
 {
     if (!h || (!draws && n_draws) || !consumed || !reverted) return set_error(LGCA_B200_EINVAL, "null argument");
-    LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     *consumed = 0;
     *reverted = 0;
     const Geom& g = h->g;
     const uint64_t num_cells = (uint64_t)g.dim_x * g.dim_y;
     if (num_cells > 0x7FFFFFFFull) return set_error(LGCA_B200_EINVAL, "body force needs < 2^31 cells (rand() range)");
-    cudaStream_t s = h->s_compute;
-    const int  model = h->cfg.model;
-    const char bf    = (char)h->cfg.bf_dir;
-    std::unordered_map<int32_t, uint8_t> touched;
-    std::vector<int32_t> cells;
+    std::vector<int32_t> cells, ch_cells;
+    std::vector<uint8_t> bytes, ch_bytes;
     size_t pos = 0;
-    uint32_t rev = 0;
-    bool done = false;
+    int64_t remaining = forcing;
+    bool first = true;
     int rc;
-    while (pos < n_draws && !done) {
-        size_t batch = (size_t)std::max<int64_t>(4096, std::min<int64_t>(1 << 20, ((int64_t)forcing - (int64_t)rev) * 12));
+    while (pos < n_draws && (first || remaining > 0)) {
+        size_t batch = (size_t)std::max<int64_t>(4096, std::min<int64_t>(1 << 20, remaining * 12));
         batch = std::min(batch, n_draws - pos);
-        if (batch > h->draw_cap) {
-            cudaFree(h->d_draws); cudaFree(h->d_draw_bytes);
-            if (h->h_draw_bytes) cudaFreeHost(h->h_draw_bytes);
-            h->d_draws = nullptr; h->d_draw_bytes = nullptr; h->h_draw_bytes = nullptr;
-            const size_t cap = std::max<size_t>(batch, 1 << 16);
-            // d_draws doubles as the scatter buffer: cap int32 cells + cap bytes
-            LGCA_CUDA_CHECK(cudaMalloc((void**)&h->d_draws, cap * 5 + 16));
-            LGCA_CUDA_CHECK(cudaMalloc((void**)&h->d_draw_bytes, cap));
-            LGCA_CUDA_CHECK(cudaHostAlloc((void**)&h->h_draw_bytes, cap, cudaHostAllocDefault));
-            h->draw_cap = cap;
-        }
-        cells.resize(batch);
-        for (size_t i = 0; i < batch; ++i) cells[i] = (int32_t)((uint64_t)(uint32_t)draws[pos + i] % num_cells);
-        LGCA_CUDA_CHECK(cudaMemcpyAsync(h->d_draws, cells.data(), batch * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-        if ((rc = launch_gather_cells(h, h->planes[h->cur], h->d_draws, batch, h->d_draw_bytes, s))) return rc;
-        LGCA_CUDA_CHECK(cudaMemcpyAsync(h->h_draw_bytes, h->d_draw_bytes, batch, cudaMemcpyDeviceToHost, s));
-        LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
-        for (size_t i = 0; i < batch && !done; ++i) {
-            const int32_t cell = cells[i];
-            uint8_t b = h->h_draw_bytes[i];
-            ++pos;
-            if (!(b & 0x80)) { // FLUID cell of this strip
-                auto it = touched.find(cell);
-                if (it != touched.end()) b = it->second;
-                uint8_t w = b;
-                if (model == LGCA_B200_HPP) {
-                    if (bf == 'x' && !(b & 1) && (b & 4)) { w = (uint8_t)((w | 1) & ~4); ++rev; }
-                    else if (bf == 'y' && (b & 2) && !(b & 8)) { w = (uint8_t)((w | 8) & ~2); ++rev; }
-                } else {
-                    if (bf == 'x' && !(b & 1) && (b & 8)) { w = (uint8_t)((w | 1) & ~8); ++rev; }
-                    else if (bf == 'y') {
-                        if ((b & 2) && !(b & 32)) { w = (uint8_t)((w | 32) & ~2); ++rev; }
-                        if ((b & 4) && !(b & 16)) { w = (uint8_t)((w | 16) & ~4); ++rev; }
-                    }
-                }
-                if (w != b) touched[cell] = w;
-            }
-            if (!((int64_t)rev < (int64_t)forcing)) done = true; // do { ... } while (reverted < forcing && ...)
-        }
-    }
-    if (!touched.empty()) {
-        const size_t n = touched.size();
-        std::vector<uint8_t> blob(n * 5);
-        int32_t* pc = reinterpret_cast<int32_t*>(blob.data());
-        uint8_t* pb = blob.data() + n * 4;
-        size_t i = 0;
-        for (auto& kv : touched) { pc[i] = kv.first; pb[i] = kv.second; ++i; }
-        if (n > h->draw_cap) return set_error(LGCA_B200_ESTATE, "internal: scatter list exceeds capacity");
-        LGCA_CUDA_CHECK(cudaMemcpyAsync(h->d_draws, blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
-        if ((rc = launch_apply_flips(h, h->planes[h->cur], h->d_draws, n, s))) return rc;
-        LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
+        cells.resize(batch); bytes.resize(batch); ch_cells.resize(batch); ch_bytes.resize(batch);
+        for (size_t i = 0; i < batch; ++i) cells[i] = (int32_t)((uint64_t)(uint32_t)draws[pos + i] % num_cells); // :269
+        if ((rc = lgca_b200_body_force_gather(h, cells.data(), batch, bytes.data()))) return rc;
+        size_t used = 0, nch = 0;
+        uint32_t rev = 0;
+        // a continuation batch must not re-run the reference's "at least one draw" rule
+        if ((rc = lgca_b200_body_force_replay(h->cfg.model, h->cfg.bf_dir, first ? (int)remaining : (int)std::max<int64_t>(remaining, 1),
+                                              cells.data(), bytes.data(), batch, &used, &rev, ch_cells.data(), ch_bytes.data(), &nch)))
+            return rc;
+        if ((rc = lgca_b200_body_force_apply(h, ch_cells.data(), ch_bytes.data(), nch))) return rc;
+        pos += used;
+        remaining -= rev;
+        *reverted += rev;
+        first = false;
     }
     *consumed = pos;
-    *reverted = rev;
     return 0;
 }
 

@@ -132,3 +132,49 @@ def test_native_ring_equals_single_lattice(model, dims, bc, nstrips, k):
         assert np.array_equal(got, o.state), "after %d steps" % done
     for e in engines:
         e.close()
+
+
+def test_body_force_on_strips():
+    """Exact body force across strips: gather on every strip, combine (minimum), ordered host replay, apply."""
+    import lgca_b200
+    from lgca_b200.capi import body_force_replay
+    from lgca_b200.ring import partition_rows
+    model, dims, nstrips = "FHP_III", (256, 96), 3
+    o = Oracle(model, dims=dims, cg=1, bf_dir=b"x", rng=OracleRng(8))
+    o.apply_bc("karman")
+    o.init("random")
+    parts = partition_rows(dims[1], nstrips, 2)
+    engines = []
+    for y0, rows in parts:
+        e = lgca_b200.Engine(model, dims[0], dims[1], bf_dir="x", k_fuse=2, y_begin=y0, y_rows=rows)
+        sl = slice(y0 * dims[0], (y0 + rows) * dims[0])
+        e.upload(o.state[sl], o.cell_type[sl], o.rnd)
+        engines.append(e)
+    o.rng = OracleRng(123)
+    g = OracleRng(123)
+    pending = []
+    n = o.num_cells
+    for forcing in (0, 3, 200, 1500):
+        used_o, rev_o = o.body_force(forcing)
+        remaining, first, used_t, rev_t = forcing, True, 0, 0
+        while first or remaining > 0:
+            want = max(512, remaining * 6)
+            while len(pending) < want:
+                pending.append(g.rand())
+            cells = (np.array(pending[:want], np.int64) % n).astype(np.int32)
+            combined = np.full(want, 0xFF, np.uint8)
+            for e in engines:
+                combined = np.minimum(combined, e.body_force_gather(cells))
+            used, rev, cc, cb = body_force_replay(model, "x", remaining if first else max(remaining, 1), cells, combined)
+            for e in engines:
+                e.body_force_apply(cc, cb)
+            del pending[:used]
+            used_t += used
+            rev_t += rev
+            remaining -= rev
+            first = False
+        assert (used_t, rev_t) == (used_o, rev_o)
+        got = np.concatenate([e.download() for e in engines])
+        assert np.array_equal(got, o.state), forcing
+    for e in engines:
+        e.close()
