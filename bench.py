@@ -426,6 +426,7 @@ def run_b200_arm(args):
         if args.workload == "periodic" and not args.no_karman:
             e.close()
             line["karman"] = karman_extra(args, peak)
+            line["diffusion_hpp"] = hpp_extra(args, peak)
     if writer:
         writer.q.put(None)
         if writer.error:
@@ -454,6 +455,26 @@ def karman_extra(args, peak):
     out = {"workload": desc, "value": dx * rows * k / (ms * 1e-3), "unit": "site updates/s", "k_fuse": k, "launch_ms": ms,
            "roofline_achieved_gbs": alg / (ms * 1e-3) / 1e9, "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak,
            "cache": "bit-planes 117 MB: partly L2-resident"}
+    e.close()
+    return out
+
+
+def hpp_extra(args, peak):
+    """Config C2 on one GPU (HPP 4096 x 4096 periodic; throughput does not depend on the particle pattern, so the
+    lattice is filled by the device initialiser instead of the diffusion disc)."""
+    import lgca_b200
+    e = lgca_b200.Engine("HPP", 4096, 4096, device=int(os.environ.get("LOCAL_RANK", "0")), k_fuse=args.k_fuse,
+                         flags=lgca_b200.capi.FLAG_NO_CELL_FIELDS)
+    e.apply_bc_device("periodic")
+    e.init_random_device(seed=1)
+    info = e.info()
+    k = info.k_fuse
+    e.timed_kernel(200)
+    ms = min(e.timed_kernel(1000) for _ in range(3))
+    alg = 4096 * 4096 * info.bytes_per_site_step_x8 / 8.0 * k
+    out = {"workload": "lgca-diffusion HPP 4096x4096 periodic (BASELINE config C2)", "value": 4096 * 4096 * k / (ms * 1e-3),
+           "unit": "site updates/s", "k_fuse": k, "launch_ms": ms, "roofline_achieved_gbs": alg / (ms * 1e-3) / 1e9,
+           "roofline_frac": alg / (ms * 1e-3) / 1e9 / peak, "cache": "bit-planes 8 MB: L2-resident"}
     e.close()
     return out
 
