@@ -16,7 +16,7 @@
 // the movers of the two triangles (even / odd directions) are counted with one full adder each, which
 // classifies every site (one mover, head-on candidate, 120-degree pair, alternating triple) in a few ops;
 // the rest-particle rules of FHP-II collapse to "flip a trio of adjacent directions and the rest bit".
-// 36 LOP3 per 32 sites for FHP-II/III (the reference's formulas lifted verbatim compile to 76).
+// 34 LOP3 per 32 sites for FHP-II/III (the reference's formulas lifted verbatim compile to 76).
 #pragma once
 #include <stdint.h>
 
@@ -88,7 +88,7 @@ LGCA_HD void collide_hpp(uint32_t (&n)[7])
 //     s_e,c_e = XOR3/MAJ(n0,n2,n4)     s_o,c_o = XOR3/MAJ(n1,n3,n5)
 // which classifies every site with a handful of 3-input ops:
 //     one even + one odd mover     g1  = s_e & s_o & ~(c_e|c_o)      (adjacent or head-on pair)
-//     alternating triple           tri = (s_e^s_o) & (c_e^c_o) & ~(s_e^c_e)
+//     alternating triple           tri = (s_e == c_e) & (s_e^s_o) & (c_e^c_o)
 // Head-on pairs are g1 & n_j & n_{j+3}; pair (j, j+3) flips with T_j = tri | h_j | (p ? h_{j+1} : h_{j+2}).
 // Rest rules (FHP-II/III).  Both fire only when ONE triangle is empty: "rest + single mover c" (the other
 // triangle holds exactly one mover) and "movers c-1, c+1, no rest" (the other triangle holds exactly two).
@@ -96,7 +96,7 @@ LGCA_HD void collide_hpp(uint32_t (&n)[7])
 // unless the vertex opposite to it (v+3, in the occupied triangle) is occupied.  Hence, with
 //     EE = even triangle empty & (r ? odd has one : odd has two),   EO = likewise with the roles swapped,
 // direction i of the even triangle becomes   EE ? ~n_{i+3} : (~EO & (n_i ^ T_i))   and symmetrically for odd i;
-// the rest bit flips when EE | EO.  36 LOP3 in total for FHP-II/III, 25 for FHP-I (counted in the SASS).
+// the rest bit flips when EE | EO.  34 LOP3 in total for FHP-II/III, 23 for FHP-I (counted in the SASS).
 // ---------------------------------------------------------------------------------------------
 template <bool WITH_REST>
 LGCA_HD void collide_fhp(uint32_t (&n)[7], uint32_t p)
@@ -105,15 +105,16 @@ LGCA_HD void collide_fhp(uint32_t (&n)[7], uint32_t p)
     const uint32_t ce = lop3<LUT_MAJ>(n[0], n[2], n[4]);
     const uint32_t so = lop3<LUT_XOR3>(n[1], n[3], n[5]);
     const uint32_t co = lop3<LUT_MAJ>(n[1], n[3], n[5]);
-    const uint32_t cor = ce | co, cxr = ce ^ co;
+    const uint32_t cor = ce | co;
     const uint32_t g1  = lop3<TA & TB & ~TC>(se, so, cor);
     // head-on pairs (reference: db1 = dirs 1,4; db2 = dirs 2,5; db3 = dirs 3,0)
     const uint32_t h1 = lop3<LUT_AND3>(n[1], n[4], g1);
     const uint32_t h2 = lop3<LUT_AND3>(n[2], n[5], g1);
     const uint32_t h3 = lop3<LUT_AND3>(n[0], n[3], g1);
-    // symmetric triple
-    const uint32_t sx  = se ^ so;
-    const uint32_t tri = lop3<TA & TB & ~TC>(sx, cxr, se ^ ce);
+    // symmetric triple: one triangle full (s = c = 1), the other empty (s = c = 0)
+    //   tri = (s_e == c_e) & (s_e ^ s_o) & (c_e ^ c_o)      -- 4 inputs, 2 ops
+    const uint32_t t1  = lop3<~(TA ^ TB) & (TA ^ TC) & 0xFF>(se, ce, so);
+    const uint32_t tri = lop3<TA & (TB ^ TC)>(t1, ce, co);
     // per-pair change masks: T14 = tri | h1 | (p ? h2 : h3), ...
     const uint32_t t14 = lop3<LUT_OR3>(tri, h1, lop3<LUT_MUX>(p, h2, h3));
     const uint32_t t25 = lop3<LUT_OR3>(tri, h2, lop3<LUT_MUX>(p, h3, h1));
