@@ -63,7 +63,6 @@ struct lgca_b200_lattice {
     void*            ring_upper_planes[2];
     void*            ring_lower_flags;
     void*            ring_upper_flags;
-    uint32_t         ring_lower_geom_rows, ring_upper_geom_rows;
     int              ring_lower_ipc, ring_upper_ipc, ring_connected;
     uint32_t         ring_epoch;
     uint64_t         ring_blocks;           // blocks issued since ring_start

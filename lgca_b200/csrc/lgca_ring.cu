@@ -183,9 +183,7 @@ int lgca_b200_ring_connect(lgca_b200_lattice* h, const void* lower_descriptor, c
         if (b->pitch != h->g.pitch || b->halo != h->g.halo || b->nd != (uint32_t)h->nd)
             return set_error(LGCA_B200_EINVAL, "neighbour strip has a different geometry (pitch/halo/planes)");
     }
-    if (lo.rows != up.rows && false) return 0;
-    // ghost-row destinations are addressed with the NEIGHBOUR's row count / plane stride
-    h->ring_lower_geom_rows = lo.rows; h->ring_upper_geom_rows = up.rows;
+    // ghost-row destinations are addressed with MY row count / plane stride: strips must have equal heights
     if (lo.plane_stride != h->g.plane_stride || up.plane_stride != h->g.plane_stride)
         return set_error(LGCA_B200_EINVAL, "native ring needs strips of equal height (plane stride differs)");
     int rc = open_peer(lo, h->cfg.device, h->ring_lower_planes, &h->ring_lower_flags);
