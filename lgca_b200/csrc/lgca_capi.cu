@@ -120,8 +120,10 @@ int lgca_b200_create(const lgca_b200_config* cfg, lgca_b200_lattice** out)
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
     h->nd  = num_dir_of(cfg->model);
-    // library default: deeper fusion pays while registers last (measured on B200: HPP 6, FHP 5)
-    h->k_fuse = cfg->k_fuse ? cfg->k_fuse : (cfg->model == LGCA_B200_HPP ? 6 : 5);
+    // default fused depth: 6; FHP lattices too small to fill the machine (< 16 M sites, e.g. the 1400 x 700 pipe)
+    // are launch-latency bound and run better with the shorter pipeline fill of 5
+    h->k_fuse = cfg->k_fuse ? cfg->k_fuse
+                            : ((cfg->model == LGCA_B200_HPP || (uint64_t)cfg->dim_x * (uint64_t)cfg->dim_y >= (1ull << 24)) ? 6 : 5);
     if (cfg->model != LGCA_B200_HPP && h->k_fuse > LGCA_MAX_K_FHP) h->k_fuse = LGCA_MAX_K_FHP;
 
     const bool whole = (cfg->y_rows == 0 || cfg->y_rows == cfg->dim_y);

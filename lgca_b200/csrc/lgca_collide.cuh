@@ -16,7 +16,7 @@
 // the movers of the two triangles (even / odd directions) are counted with one full adder each, which
 // classifies every site (one mover, head-on candidate, 120-degree pair, alternating triple) in a few ops;
 // the rest-particle rules of FHP-II collapse to "flip a trio of adjacent directions and the rest bit".
-// 34 LOP3 per 32 sites for FHP-II/III (the reference's formulas lifted verbatim compile to 76).
+// 31 LOP3 per 32 sites for FHP-II/III (the reference's formulas lifted verbatim compile to 76).
 #pragma once
 #include <stdint.h>
 
@@ -87,16 +87,17 @@ LGCA_HD void collide_hpp(uint32_t (&n)[7])
 // with one full adder each:
 //     s_e,c_e = XOR3/MAJ(n0,n2,n4)     s_o,c_o = XOR3/MAJ(n1,n3,n5)
 // which classifies every site with a handful of 3-input ops:
-//     one even + one odd mover     g1  = s_e & s_o & ~(c_e|c_o)      (adjacent or head-on pair)
+//     head-on pair somewhere       HO  = s_e & s_o & ~c_e & (n0 == n3) & (n1 == n4)
 //     alternating triple           tri = (s_e == c_e) & (s_e^s_o) & (c_e^c_o)
-// Head-on pairs are g1 & n_j & n_{j+3}; pair (j, j+3) flips with T_j = tri | h_j | (p ? h_{j+1} : h_{j+2}).
+// Pair (j, j+3) flips with T_j = tri | (HO & ~(p ? n_{j+2} : n_{j+1})): under HO exactly one pair is full and
+// only the pair it does NOT rotate onto stays unchanged (no per-pair head-on signals are needed).
 // Rest rules (FHP-II/III).  Both fire only when ONE triangle is empty: "rest + single mover c" (the other
 // triangle holds exactly one mover) and "movers c-1, c+1, no rest" (the other triangle holds exactly two).
 // In both, the occupied triangle is cleared of what it holds, and every vertex v of the EMPTY triangle is set
 // unless the vertex opposite to it (v+3, in the occupied triangle) is occupied.  Hence, with
 //     EE = even triangle empty & (r ? odd has one : odd has two),   EO = likewise with the roles swapped,
 // direction i of the even triangle becomes   EE ? ~n_{i+3} : (~EO & (n_i ^ T_i))   and symmetrically for odd i;
-// the rest bit flips when EE | EO.  34 LOP3 in total for FHP-II/III, 23 for FHP-I (counted in the SASS).
+// the rest bit flips when EE | EO.  31 LOP3 in total for FHP-II/III, 20 for FHP-I (counted in the SASS).
 // ---------------------------------------------------------------------------------------------
 template <bool WITH_REST>
 LGCA_HD void collide_fhp(uint32_t (&n)[7], uint32_t p)
@@ -105,20 +106,27 @@ LGCA_HD void collide_fhp(uint32_t (&n)[7], uint32_t p)
     const uint32_t ce = lop3<LUT_MAJ>(n[0], n[2], n[4]);
     const uint32_t so = lop3<LUT_XOR3>(n[1], n[3], n[5]);
     const uint32_t co = lop3<LUT_MAJ>(n[1], n[3], n[5]);
-    const uint32_t cor = ce | co;
-    const uint32_t g1  = lop3<TA & TB & ~TC>(se, so, cor);
-    // head-on pairs (reference: db1 = dirs 1,4; db2 = dirs 2,5; db3 = dirs 3,0)
-    const uint32_t h1 = lop3<LUT_AND3>(n[1], n[4], g1);
-    const uint32_t h2 = lop3<LUT_AND3>(n[2], n[5], g1);
-    const uint32_t h3 = lop3<LUT_AND3>(n[0], n[3], g1);
+    // head-on pair somewhere: one even and one odd mover (s_e & s_o, no carry) sitting opposite each other.
+    // With s_e & s_o, "pairs (0,3) and (1,4) are each empty or full" leaves exactly the three head-on states and
+    // the all-six state, which ~c_e removes.  3 ops, no per-pair head-on signals.
+    const uint32_t u0 = lop3<TA & ~(TB ^ TC) & 0xFF>(se, n[0], n[3]);
+    const uint32_t u1 = lop3<TA & ~(TB ^ TC) & 0xFF>(so, n[1], n[4]);
+    const uint32_t HO = lop3<TA & TB & ~TC & 0xFF>(u0, u1, ce);
     // symmetric triple: one triangle full (s = c = 1), the other empty (s = c = 0)
     //   tri = (s_e == c_e) & (s_e ^ s_o) & (c_e ^ c_o)      -- 4 inputs, 2 ops
     const uint32_t t1  = lop3<~(TA ^ TB) & (TA ^ TC) & 0xFF>(se, ce, so);
     const uint32_t tri = lop3<TA & (TB ^ TC)>(t1, ce, co);
-    // per-pair change masks: T14 = tri | h1 | (p ? h2 : h3), ...
-    const uint32_t t14 = lop3<LUT_OR3>(tri, h1, lop3<LUT_MUX>(p, h2, h3));
-    const uint32_t t25 = lop3<LUT_OR3>(tri, h2, lop3<LUT_MUX>(p, h3, h1));
-    const uint32_t t30 = lop3<LUT_OR3>(tri, h3, lop3<LUT_MUX>(p, h1, h2));
+    // per-pair change masks.  Under HO exactly one pair k is full (n_k = n_{k+3} = 1, everything else empty) and it
+    // rotates onto pair k+1 (p = 0) or k-1 (p = 1): pair j flips unless it is the third pair, i.e. unless
+    // pair j+1 (p = 0) / pair j+2 (p = 1) is the full one:   T_j = tri | (HO & ~(p ? n_{j+2} : n_{j+1}))
+    // (reference: db1 = dirs 1,4; db2 = dirs 2,5; db3 = dirs 3,0).  Written out that is 6 ops; the 5-op form below
+    // was found by exhaustive search over LOP3 networks (scripts/lop3_search.c, block "T"):
+    //   nc  = no collision;  q = tri ? ~n0 : (p ^ n0);  T_1, T_2 from (n4 | n5, nc, q);  T_0 = f(tri, T_1, T_2)
+    const uint32_t nc  = lop3<0x03>(tri, HO, p);        // ~tri & ~HO
+    const uint32_t q   = lop3<0x56>(tri, p, n[0]);
+    const uint32_t t14 = lop3<0x32>(n[4], nc, q);
+    const uint32_t t25 = lop3<0x31>(n[5], nc, q);
+    const uint32_t t30 = lop3<0x86>(tri, t14, t25);
 
     if (WITH_REST) {
         const uint32_t r  = n[6];

@@ -28,13 +28,36 @@ namespace lgca_b200 {
 
 constexpr int WAVE_VALID = 30; // interior lanes per warp
 
-__device__ __forceinline__ uint32_t up1(uint32_t w)   // site x <- site x-1
+// x-streaming by one site.  The neighbour lane's word comes by warp shuffle; the 1-bit funnel shift itself is
+// either a SHF (integer pipe) or, with LGCA_FMA_SHIFT (default), two multiply-adds on the otherwise idle FMA pipe:
+//     (w << 1) | (nb >> 31)  =  w * 2    + hi32(nb * 2)            IMAD + IMAD.HI
+//     (w >> 1) | (nb << 31)  =  hi32(w * 2^31) + nb * 2^31          IMAD.HI + IMAD
+// (the two summands never share a bit, so + is |).  The integer pipe is this kernel's limiter (LOP3), and SHF
+// were 10 % of its work.  The multipliers are kernel ARGUMENTS: with literal constants ptxas strength-reduces the
+// products back into SHF / LEA.
+#ifndef LGCA_FMA_SHIFT
+#define LGCA_FMA_SHIFT 0
+#endif
+#ifndef LGCA_STRIDED_STORES
+#define LGCA_STRIDED_STORES 1
+#endif
+__device__ __forceinline__ uint32_t up1(uint32_t w, uint32_t two)   // site x <- site x-1
 {
-    return __funnelshift_l(__shfl_up_sync(0xFFFFFFFFu, w, 1), w, 1);
+    const uint32_t nb = __shfl_up_sync(0xFFFFFFFFu, w, 1);
+#if LGCA_FMA_SHIFT
+    return w * two + __umulhi(nb, two);
+#else
+    return __funnelshift_l(nb, w, 1);
+#endif
 }
-__device__ __forceinline__ uint32_t down1(uint32_t w) // site x <- site x+1
+__device__ __forceinline__ uint32_t down1(uint32_t w, uint32_t half) // site x <- site x+1
 {
-    return __funnelshift_r(w, __shfl_down_sync(0xFFFFFFFFu, w, 1), 1);
+    const uint32_t nb = __shfl_down_sync(0xFFFFFFFFu, w, 1);
+#if LGCA_FMA_SHIFT
+    return __umulhi(w, half) + nb * half;
+#else
+    return __funnelshift_r(w, nb, 1);
+#endif
 }
 
 // Kernel arguments: per-plane base pointers live in the constant parameter bank, so an address is one
@@ -49,6 +72,8 @@ struct WaveArgs {
     // native ring: tiles that read ghost rows spin until the neighbours have published `ring_epoch`
     const uint32_t* ring_flags; // [0] from the lower neighbour, [1] from the upper; nullptr = no in-kernel wait
     uint32_t        ring_epoch;
+    uint32_t        stride_bytes;      // distance between consecutive planes of a set (in[d] = in[0] + d * stride)
+    uint32_t        mul_two, mul_half; // 2 and 2^31: run-time multipliers of the FMA-pipe funnel shifts (up1/down1)
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
@@ -79,6 +104,23 @@ struct LaneSrc {
         }
         return v;
     }
+    // All ND planes of one row.  The planes of a set are equally spaced (`stride_bytes` apart), so the row address is
+    // formed ONCE (one constant-bank base + IMAD.WIDE) and every further plane is a single IMAD.WIDE
+    // (stride * d + row pointer) -- no per-plane constant-bank pointer load.
+    template <int ND>
+    __device__ __forceinline__ void load_planes(uint32_t (&v)[7], const uint32_t* __restrict__ plane0, uint32_t stride_bytes,
+                                                uint32_t row_off) const
+    {
+        if (!IRREG) {
+            const char* pr = (const char*)(plane0 + (row_off + wa));
+#pragma unroll
+            for (int d = 0; d < ND; ++d) v[d] = __ldg((const uint32_t*)(pr + (uint64_t)stride_bytes * (uint32_t)d));
+        } else {
+#pragma unroll
+            for (int d = 0; d < ND; ++d)
+                v[d] = load((const uint32_t*)((const char*)plane0 + (uint64_t)stride_bytes * (uint32_t)d), row_off);
+        }
+    }
 };
 
 // Everything one lane carries through the row loop.
@@ -91,16 +133,17 @@ struct WaveState {
     uint32_t nx2[7];                 // prefetched level-0 row r0 + 2 (loads stay in flight for a whole iteration)
     uint32_t pm1, pns1, psl1;        // prefetched mask words of row r0 + 1
     uint32_t Mp[K], Mns[K], Msl[K];  // mask words of the rows the levels produce next: index s-1 <-> row r0 - s
-    uint32_t r0m;                    // stored index of the level-0 row that arrived last
-    uint32_t pf, pf_left;            // stored index of the last level-0 row fetched / rows still to fetch
+    uint32_t r0m;                    // stored index of the level-0 row that arrived last (slip walls only)
+    uint32_t ro;                     // word offset of the last level-0 row fetched
 };
 
 // One iteration: level-0 row r0 arrives, every level s produces its row r0 - s, and the level-K row
 // r0 - K is stored.  PAR = parity of the iteration index (compile time); WARM = pipeline still filling
 // (levels whose inputs are not there yet are skipped, nothing is stored before iteration 2K).
 template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG, int PAR, bool WARM>
-__device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>& src, int jc, uint32_t out_off,
-                                         const WaveArgs& A, const Geom& g, uint32_t ew, bool store_lane, uint32_t vmask)
+__device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>& src, int jc, int fetch_end,
+                                         uint32_t plane_words, uint32_t out_off, const WaveArgs& A, const Geom& g,
+                                         uint32_t ew, bool store_lane, uint32_t vmask)
 {
     constexpr int  ND  = num_dir_of(MODEL);
     constexpr bool HPP = rule_of(MODEL) == MODEL_HPP;
@@ -112,18 +155,17 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>&
     // mask words of the arriving row r0 (prefetched one iteration ago); level 1 uses them next iteration
     const uint32_t pm = st.pm1, pns = st.pns1, psl = st.psl1;
 
-    if (++st.r0m >= rows) st.r0m -= rows; // stored index of the arriving row r0
+    if (HAS_SL) { if (++st.r0m >= rows) st.r0m -= rows; } // stored index of the arriving row r0 (slip walls only)
     // Prefetch TWO rows ahead: level-0 row r0 + 2 and the mask words of row r0 + 1.  The loads have a whole
     // iteration to land wherever the scheduler places them.
     {
-        uint32_t r1 = st.r0m + 1; if (r1 >= rows) r1 -= rows;
+        // the mask row r0 + 1 is the row the planes were prefetched from one iteration ago
+        const uint32_t rm = st.ro;
         // never fetch past the tile's last input row (the last fetch is simply repeated): ghost rows of a strip
         // are only ever read by tiles that waited for them
-        if (st.pf_left) { --st.pf_left; if (++st.pf >= rows) st.pf -= rows; }
-        const uint32_t ro = st.pf * g.pitch;
-#pragma unroll
-        for (int d = 0; d < ND; ++d) st.nx2[d] = src.load(A.in[d], ro);
-        const uint32_t rm = r1 * g.pitch;
+        if (jc < fetch_end) { st.ro += g.pitch; if (st.ro >= plane_words) st.ro -= plane_words; }
+        const uint32_t ro = st.ro;
+        src.template load_planes<ND>(st.nx2, A.in[0], A.stride_bytes, ro);
         if (!HPP) st.pm1 = src.load(A.ch, rm);
         if (HAS_NS) st.pns1 = src.load(A.ns, rm);
         if (HAS_SL) st.psl1 = src.load(A.sl, rm);
@@ -138,23 +180,23 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>&
             // ya is even and stored-row parity equals global parity (halo and y0 are even)
             const bool odd = ((K + PAR + s) & 1) != 0;
             if (HPP) {
-                n[0] = up1(st.C0[s - 1]);
-                n[2] = down1(st.C2[s - 1]);
+                n[0] = up1(st.C0[s - 1], A.mul_two);
+                n[2] = down1(st.C2[s - 1], A.mul_half);
                 n[1] = st.D1[s - 1];      // plane 1 of row y-1
                 n[3] = a[3];              // plane 3 of row y+1
             } else {
-                n[0] = up1(st.C0[s - 1]);
-                n[3] = down1(st.C3[s - 1]);
+                n[0] = up1(st.C0[s - 1], A.mul_two);
+                n[3] = down1(st.C3[s - 1], A.mul_half);
                 if (ND == 7) n[6] = st.C6[s - 1];
                 if (!odd) {
-                    n[1] = up1(st.D1[s - 1]);
+                    n[1] = up1(st.D1[s - 1], A.mul_two);
                     n[2] = st.D2[s - 1];
                     n[4] = a[4];
-                    n[5] = up1(a[5]);
+                    n[5] = up1(a[5], A.mul_two);
                 } else {
                     n[1] = st.D1[s - 1];
-                    n[2] = down1(st.D2[s - 1]);
-                    n[4] = down1(a[4]);
+                    n[2] = down1(st.D2[s - 1], A.mul_half);
+                    n[4] = down1(a[4], A.mul_half);
                     n[5] = a[5];
                 }
             }
@@ -205,21 +247,39 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>&
     st.Mp[0] = pm; st.Mns[0] = pns; st.Msl[0] = psl;
 
     if ((!WARM || jc >= 2 * K) && store_lane) {
+#if LGCA_STRIDED_STORES
+        char* po = (char*)(A.out[0] + out_off);
+#pragma unroll
+        for (int d = 0; d < ND; ++d) *(uint32_t*)(po + (uint64_t)A.stride_bytes * (uint32_t)d) = IRREG ? (a[d] & vmask) : a[d];
+#else
 #pragma unroll
         for (int d = 0; d < ND; ++d) A.out[d][out_off] = IRREG ? (a[d] & vmask) : a[d];
+#endif
     }
 }
 
+// Register cap via the resident-blocks hint: the all-fluid FHP variants (K <= 5) fit 96 registers without a single
+// spill, which lifts the occupancy from 18 to 21 one-warp blocks per SM; the wall variants and K = 6 would spill
+// inside the row loop and HPP needs only 64 registers, so they carry no hint (0).
+#ifndef LGCA_WAVE_MIN_BLOCKS
+#define LGCA_WAVE_MIN_BLOCKS 20
+#endif
 template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
-__global__ void __launch_bounds__(32) step_wave_kernel(const WaveArgs A, const Geom g, const WavePlan wp)
+constexpr int wave_min_blocks()
+{
+    return (rule_of(MODEL) != MODEL_HPP && !HAS_NS && !HAS_SL && !IRREG && K <= 5) ? LGCA_WAVE_MIN_BLOCKS : 0; // 0 = no hint
+}
+template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
+__global__ void __launch_bounds__(32, wave_min_blocks<MODEL, K, HAS_NS, HAS_SL, IRREG>()) step_wave_kernel(const WaveArgs A, const Geom g, const WavePlan wp)
 {
     constexpr int ND = num_dir_of(MODEL);
     const int lane = threadIdx.x;
     // one warp per block: the tile index (and with it every loop bound) is provably warp-uniform, so the
     // shuffles in the row loop compile to plain SHFL without convergence bookkeeping
-    const int tile = blockIdx.x;
-    const int band  = tile % wp.bands;
-    const int c    = tile / wp.bands;
+    // 2-D grid (x = band, y = chunk; blocks are issued x-fastest, so the chunk order is the schedule order): no
+    // division, so every row index below stays on the uniform datapath
+    const int band = blockIdx.x;
+    const int c    = blockIdx.y;
     // Row range [ya, yb) of this tile's output, relative to the first owned row.  Whole lattices: uniform chunks.
     // Strips: tile rows 0 and 1 are the bottom and the top EDGE chunk (the only ones that read ghost rows); they are
     // scheduled first and are shorter than the interior chunks, so that waiting for the neighbours' ghost rows at
@@ -303,13 +363,14 @@ __global__ void __launch_bounds__(32) step_wave_kernel(const WaveArgs A, const G
         st.psl1 = HAS_SL ? src.load(A.sl, ro) : 0u;
     }
     st.r0m = (uint32_t)(r0 == 0 ? rows - 1 : r0 - 1); // wave_row advances it to the arriving row first thing
-    st.pf = (uint32_t)(r0 + 1 >= rows ? r0 + 1 - rows : r0 + 1);
-    st.pf_left = (uint32_t)(total - 2);
+    st.ro = (uint32_t)(r0 + 1 >= rows ? r0 + 1 - rows : r0 + 1) * g.pitch;
+    const int      fetch_end   = total - 2;             // iterations 0 .. total-3 fetch a new row (r0 + 2)
+    const uint32_t plane_words = g.rows * g.pitch;
 
     // word offset of the row stored by the current iteration (row ya - 2K + jc), advanced per row
     uint32_t out_off = (uint32_t)ya * g.pitch + (uint32_t)max(wi, 0);
 #define LGCA_ROW(PAR, WARM, JC)                                                                                      \
-    wave_row<MODEL, K, HAS_NS, HAS_SL, IRREG, PAR, WARM>(st, src, JC, out_off, A, g, ew, store_lane, vmask)
+    wave_row<MODEL, K, HAS_NS, HAS_SL, IRREG, PAR, WARM>(st, src, JC, fetch_end, plane_words, out_off, A, g, ew, store_lane, vmask)
     // pipeline fill: iterations 0 .. 2K-1 store nothing (2K is even, so parities alternate from 0)
 #pragma unroll 1
     for (int j = 0; j < 2 * K; j += 2) {
@@ -346,6 +407,7 @@ static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
     double best = 1e300;
     for (int cr = 2 * k; cr <= rows + 1; cr += 2) {
         const int    chunks = (rows + cr - 1) / cr;
+        if (chunks + 2 > 65535) continue; // chunks ride in gridDim.y
         const double w      = (double)chunks * wp.bands / 148.0; // warps per SM
         const double rounds = fmax(1.0, ceil(w / resident));
         const double eff    = pow(fmin(1.0, (w / rounds) / resident), 0.6);
@@ -406,8 +468,11 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
     A.ns = h->ns; A.sl = h->sl; A.ch = h->ch; A.xedge = h->xedge;
     A.ring_flags = h->ring_inkernel_epoch ? (const uint32_t*)h->ring_flags : nullptr;
     A.ring_epoch = h->ring_inkernel_epoch;
+    A.mul_two = 2u; A.mul_half = 0x80000000u;
+    A.stride_bytes = (uint32_t)(h->g.plane_stride * sizeof(uint32_t));
     if (!in) return 0; // prepare only (wave_prepare): plan + module load, no launch
-    kernel<<<dim3(wp.tiles, 1, 1), dim3(32, 1, 1), 0, s>>>(A, h->g, wp);
+    if (wp.chunks > 65535) return set_error(LGCA_B200_EINVAL, "chunk plan exceeds gridDim.y (%d chunks)", wp.chunks);
+    kernel<<<dim3(wp.bands, wp.chunks, 1), dim3(32, 1, 1), 0, s>>>(A, h->g, wp);
     h->launches++;
     LGCA_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -416,7 +481,8 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
 template <int MODEL, int K>
 static int launch_mk(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s)
 {
-    if ((uint64_t)h->g.rows * h->g.pitch > 0xFFFFFFFFull) return set_error(LGCA_B200_EINVAL, "plane too large for 32-bit word offsets");
+    if ((uint64_t)h->g.rows * h->g.pitch > 0xFFFFFFFFull || (uint64_t)h->g.plane_stride * sizeof(uint32_t) > 0xFFFFFFFFull)
+        return set_error(LGCA_B200_EINVAL, "plane too large for 32-bit word offsets");
     const bool irreg = h->g.rem != 0;
 #define GO(NS, SL) (irreg ? launch_variant<MODEL, K, NS, SL, true>(h, in, out, s) : launch_variant<MODEL, K, NS, SL, false>(h, in, out, s))
     if (h->has_sl) return h->has_ns ? GO(true, true) : GO(false, true);
