@@ -120,6 +120,8 @@ int lgca_b200_create(const lgca_b200_config* cfg, lgca_b200_lattice** out)
     memset(h, 0, sizeof(*h));
     h->cfg = *cfg;
     h->nd  = num_dir_of(cfg->model);
+    pthread_mutex_init(&h->snap_mutex, nullptr);
+    h->snap_mutex_init = 1;
     // default fused depth: 6; FHP lattices too small to fill the machine (< 16 M sites, e.g. the 1400 x 700 pipe)
     // are launch-latency bound and run better with the shorter pipeline fill of 5
     h->k_fuse = cfg->k_fuse ? cfg->k_fuse
@@ -199,6 +201,7 @@ int lgca_b200_destroy(lgca_b200_lattice* h)
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_post) cudaStreamDestroy(h->s_post);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    if (h->snap_mutex_init) pthread_mutex_destroy(&h->snap_mutex);
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
     if (h->ev_post) cudaEventDestroy(h->ev_post);
     if (h->ev_t0) cudaEventDestroy(h->ev_t0);
@@ -352,6 +355,7 @@ int lgca_b200_snapshot(lgca_b200_lattice* h)
 {
     if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+    SnapLock lock(h);
     // do not overwrite the snapshot while the post stream still reads it
     LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_post, 0));
     // native ring: the ghost rows of the live buffer are written by the neighbours; the coarse means of the top
@@ -375,6 +379,7 @@ int lgca_b200_post_process(lgca_b200_lattice* h, float* cell_density, float* cel
     cudaStream_t s = h->s_post;
     const size_t cells = (size_t)g.dim_x * own_rows(h);
     int rc;
+    SnapLock lock(h);
     LGCA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_snap, 0));
     if (cell_density || cell_momentum) {
         if (h->cfg.flags & LGCA_B200_FLAG_NO_CELL_FIELDS)
@@ -404,6 +409,7 @@ int lgca_b200_post_process(lgca_b200_lattice* h, float* cell_density, float* cel
             LGCA_CUDA_CHECK(cudaMemcpyAsync(mean_momentum, h->d_mean_momentum, 2 * nc * sizeof(float), cudaMemcpyDeviceToHost, s));
     }
     LGCA_CUDA_CHECK(cudaEventRecord(h->ev_post, s));
+    lock.release(); // the stepping thread may snapshot again: its copy is ordered behind ev_post on the device
     LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
     return 0;
 }
@@ -413,11 +419,13 @@ int lgca_b200_mean_velocity(lgca_b200_lattice* h, float out[2])
     if (!h || !out) return set_error(LGCA_B200_EINVAL, "null argument");
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     cudaStream_t s = h->s_post;
+    SnapLock lock(h);
     LGCA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_snap, 0));
     int rc = launch_mean_velocity(h, h->snap, h->d_scalars, s);
     if (rc) return rc;
     LGCA_CUDA_CHECK(cudaMemcpyAsync(h->h_scalars, h->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
     LGCA_CUDA_CHECK(cudaEventRecord(h->ev_post, s));
+    lock.release();
     LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
     const double n = h->h_scalars[2];
     out[0] = (float)(h->h_scalars[0] / n);

@@ -1,6 +1,7 @@
 // Internal (library-private) declarations: the handle behind lgca_b200_lattice and the kernel
 // launchers implemented in the individual .cu files.
 #pragma once
+#include <pthread.h>
 #include <stdint.h>
 #include <cuda_runtime.h>
 
@@ -40,6 +41,12 @@ struct lgca_b200_lattice {
     cudaStream_t     s_copy;                 // PCIe copies of upload/download, pipelined against pack/unpack
     cudaEvent_t      ev_stage_free[2], ev_stage_full[2];
     cudaEvent_t      ev_snap, ev_post, ev_t0, ev_t1;
+    // Two host threads may drive one handle (stepping + snapshot on one, post_process / mean_velocity on the other,
+    // apps/pipe/pipe_viewer.cpp:105,150).  The device-side ordering between "snapshot overwrites the buffer" and
+    // "the post stream reads it" rests on ev_snap / ev_post, and an event wait only sees records that were enqueued
+    // BEFORE it: this mutex makes "wait + enqueue + record" atomic on the host for both sides.
+    pthread_mutex_t  snap_mutex;
+    int              snap_mutex_init;
     // staging (lazily allocated, reused)
     void*            d_stage[2];
     size_t           stage_bytes;
@@ -72,6 +79,15 @@ struct lgca_b200_lattice {
 };
 
 namespace lgca_b200 {
+
+struct SnapLock { // scoped lock of snap_mutex (early returns of the CUDA-check macros release it)
+    pthread_mutex_t* m;
+    explicit SnapLock(lgca_b200_lattice* h) : m(&h->snap_mutex) { pthread_mutex_lock(m); }
+    ~SnapLock() { if (m) pthread_mutex_unlock(m); }
+    void release() { if (m) { pthread_mutex_unlock(m); m = nullptr; } }
+    SnapLock(const SnapLock&) = delete;
+    SnapLock& operator=(const SnapLock&) = delete;
+};
 
 // lgca_step_simple.cu : one 32-site word per thread, one step per pass
 int launch_step_simple(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s);

@@ -106,19 +106,19 @@ struct LaneSrc {
     }
     // All ND planes of one row.  The planes of a set are equally spaced (`stride_bytes` apart), so the row address is
     // formed ONCE (one constant-bank base + IMAD.WIDE) and every further plane is a single IMAD.WIDE
-    // (stride * d + row pointer) -- no per-plane constant-bank pointer load.
+    // (stride * d + row pointer) -- no per-plane constant-bank pointer load.  Widths that are not a multiple of 32
+    // keep the per-plane pointers (their edge lanes assemble a word from up to three loads).
     template <int ND>
-    __device__ __forceinline__ void load_planes(uint32_t (&v)[7], const uint32_t* __restrict__ plane0, uint32_t stride_bytes,
+    __device__ __forceinline__ void load_planes(uint32_t (&v)[7], const uint32_t* const (&planes)[7], uint32_t stride_bytes,
                                                 uint32_t row_off) const
     {
         if (!IRREG) {
-            const char* pr = (const char*)(plane0 + (row_off + wa));
+            const char* pr = (const char*)(planes[0] + (row_off + wa));
 #pragma unroll
             for (int d = 0; d < ND; ++d) v[d] = __ldg((const uint32_t*)(pr + (uint64_t)stride_bytes * (uint32_t)d));
         } else {
 #pragma unroll
-            for (int d = 0; d < ND; ++d)
-                v[d] = load((const uint32_t*)((const char*)plane0 + (uint64_t)stride_bytes * (uint32_t)d), row_off);
+            for (int d = 0; d < ND; ++d) v[d] = load(planes[d], row_off);
         }
     }
 };
@@ -165,7 +165,7 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>&
         // are only ever read by tiles that waited for them
         if (jc < fetch_end) { st.ro += g.pitch; if (st.ro >= plane_words) st.ro -= plane_words; }
         const uint32_t ro = st.ro;
-        src.template load_planes<ND>(st.nx2, A.in[0], A.stride_bytes, ro);
+        src.template load_planes<ND>(st.nx2, A.in, A.stride_bytes, ro);
         if (!HPP) st.pm1 = src.load(A.ch, rm);
         if (HAS_NS) st.pns1 = src.load(A.ns, rm);
         if (HAS_SL) st.psl1 = src.load(A.sl, rm);
@@ -247,27 +247,39 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>&
     st.Mp[0] = pm; st.Mns[0] = pns; st.Msl[0] = psl;
 
     if ((!WARM || jc >= 2 * K) && store_lane) {
-#if LGCA_STRIDED_STORES
-        char* po = (char*)(A.out[0] + out_off);
+        if (LGCA_STRIDED_STORES && !IRREG) {
+            char* po = (char*)(A.out[0] + out_off); // same addressing scheme as load_planes
 #pragma unroll
-        for (int d = 0; d < ND; ++d) *(uint32_t*)(po + (uint64_t)A.stride_bytes * (uint32_t)d) = IRREG ? (a[d] & vmask) : a[d];
-#else
+            for (int d = 0; d < ND; ++d) *(uint32_t*)(po + (uint64_t)A.stride_bytes * (uint32_t)d) = a[d];
+        } else {
 #pragma unroll
-        for (int d = 0; d < ND; ++d) A.out[d][out_off] = IRREG ? (a[d] & vmask) : a[d];
-#endif
+            for (int d = 0; d < ND; ++d) A.out[d][out_off] = IRREG ? (a[d] & vmask) : a[d];
+        }
     }
 }
 
-// Register cap via the resident-blocks hint: the all-fluid FHP variants (K <= 5) fit 96 registers without a single
-// spill, which lifts the occupancy from 18 to 21 one-warp blocks per SM; the wall variants and K = 6 would spill
-// inside the row loop and HPP needs only 64 registers, so they carry no hint (0).
+// Register cap via the resident-blocks hint.  One-warp blocks are spread over the four SM sub-partitions of 16384
+// registers each, so the occupancy steps are 128 registers -> 4 warps per sub-partition, 96 -> 5, 80 -> 6.  The
+// all-fluid FHP variants (K <= 5) fit 96 registers with at most two spilled words, which lifts them from 4 to 5
+// resident warps per scheduler (+7 % measured); the wall variants and K = 6 would spill 10-40 words inside the row
+// loop and HPP needs only 64 registers, so they carry no hint (0).
 #ifndef LGCA_WAVE_MIN_BLOCKS
 #define LGCA_WAVE_MIN_BLOCKS 20
+#endif
+#ifndef LGCA_WAVE_MIN_BLOCKS_LOWK   // K <= 4 (A/B experiments: 24 = 80 registers)
+#define LGCA_WAVE_MIN_BLOCKS_LOWK LGCA_WAVE_MIN_BLOCKS
+#endif
+#ifndef LGCA_WAVE_CAP_NS            // 1: the no-slip wall variants carry the hint too (A/B experiments)
+#define LGCA_WAVE_CAP_NS 0
+#endif
+#ifndef LGCA_WAVE_CAP_KMAX          // deepest K that carries the hint
+#define LGCA_WAVE_CAP_KMAX 5
 #endif
 template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
 constexpr int wave_min_blocks()
 {
-    return (rule_of(MODEL) != MODEL_HPP && !HAS_NS && !HAS_SL && !IRREG && K <= 5) ? LGCA_WAVE_MIN_BLOCKS : 0; // 0 = no hint
+    return (rule_of(MODEL) != MODEL_HPP && (!HAS_NS || LGCA_WAVE_CAP_NS) && !HAS_SL && !IRREG && K <= LGCA_WAVE_CAP_KMAX)
+               ? (K <= 4 ? LGCA_WAVE_MIN_BLOCKS_LOWK : LGCA_WAVE_MIN_BLOCKS) : 0; // 0 = no hint
 }
 template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
 __global__ void __launch_bounds__(32, wave_min_blocks<MODEL, K, HAS_NS, HAS_SL, IRREG>()) step_wave_kernel(const WaveArgs A, const Geom g, const WavePlan wp)
