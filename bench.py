@@ -383,7 +383,7 @@ def run_b200_arm(args):
                 "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "kernel": "step_wave_kernel<FHP_II rule, K=%d>" % k,
                 "launch_ms": kms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "dram_frac": (traffic / (kms * 1e-3) / 1e9 / peak) if traffic else None,
-                "limiter": "integer pipe (LOP3/SHF): sm__pipe_alu ~80% active in profiles/, DRAM ~50% of the copy peak",
+                "limiter": "integer pipe + issue slots (LOP3/SHF/SHFL; sm__pipe_alu and issue_active in profiles/), not DRAM: dram_frac is the share of the copy peak the kernel really moves",
                 "note": "algorithmic bytes = sites*(2*NUM_DIR+masks)/8 per step x k fused steps per launch; "
                         "real DRAM traffic (`traffic`, ncu) is ~1/k of it (temporal blocking), so frac exceeds 1; "
                         "dram_frac = traffic / launch time / peak"}

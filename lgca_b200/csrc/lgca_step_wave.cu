@@ -28,18 +28,16 @@ namespace lgca_b200 {
 
 constexpr int WAVE_VALID = 30; // interior lanes per warp
 
-// x-streaming by one site.  The neighbour lane's word comes by warp shuffle; the 1-bit funnel shift itself is
-// either a SHF (integer pipe) or, with LGCA_FMA_SHIFT (default), two multiply-adds on the otherwise idle FMA pipe:
+// x-streaming by one site.  The neighbour lane's word comes by warp shuffle, the 1-bit funnel shift is a SHF.
+// Measured alternative (-DLGCA_FMA_SHIFT=1): two multiply-adds on the otherwise idle FMA pipe,
 //     (w << 1) | (nb >> 31)  =  w * 2    + hi32(nb * 2)            IMAD + IMAD.HI
 //     (w >> 1) | (nb << 31)  =  hi32(w * 2^31) + nb * 2^31          IMAD.HI + IMAD
-// (the two summands never share a bit, so + is |).  The integer pipe is this kernel's limiter (LOP3), and SHF
-// were 10 % of its work.  The multipliers are kernel ARGUMENTS: with literal constants ptxas strength-reduces the
-// products back into SHF / LEA.
+// (the summands never share a bit, so + is |; the multipliers must be kernel ARGUMENTS, with literals ptxas
+// strength-reduces the products back into SHF / LEA).  It takes 40 of 366 instructions per loop body off the
+// integer pipe but adds 40 issue slots, and on B200 it is 3 % SLOWER (C5: 104.9 vs 101.5 us per update): the loop
+// is bound by issue slots + integer pipe together, not by the integer pipe alone.
 #ifndef LGCA_FMA_SHIFT
 #define LGCA_FMA_SHIFT 0
-#endif
-#ifndef LGCA_STRIDED_STORES
-#define LGCA_STRIDED_STORES 1
 #endif
 __device__ __forceinline__ uint32_t up1(uint32_t w, uint32_t two)   // site x <- site x-1
 {
@@ -247,7 +245,7 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>&
     st.Mp[0] = pm; st.Mns[0] = pns; st.Msl[0] = psl;
 
     if ((!WARM || jc >= 2 * K) && store_lane) {
-        if (LGCA_STRIDED_STORES && !IRREG) {
+        if (!IRREG) {
             char* po = (char*)(A.out[0] + out_off); // same addressing scheme as load_planes
 #pragma unroll
             for (int d = 0; d < ND; ++d) *(uint32_t*)(po + (uint64_t)A.stride_bytes * (uint32_t)d) = a[d];
@@ -261,25 +259,16 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>&
 // Register cap via the resident-blocks hint.  One-warp blocks are spread over the four SM sub-partitions of 16384
 // registers each, so the occupancy steps are 128 registers -> 4 warps per sub-partition, 96 -> 5, 80 -> 6.  The
 // all-fluid FHP variants (K <= 5) fit 96 registers with at most two spilled words, which lifts them from 4 to 5
-// resident warps per scheduler (+7 % measured); the wall variants and K = 6 would spill 10-40 words inside the row
-// loop and HPP needs only 64 registers, so they carry no hint (0).
+// resident warps per scheduler (+7 % measured).  Measured and rejected: K = 6 at 96 registers (11 spilled words,
+// -1.4 %), the wall variants at 96 (33-43 spilled words, -11 %), K = 4 at 80 registers (-4 %); HPP needs only 64.
+// Those variants carry no hint (0).
 #ifndef LGCA_WAVE_MIN_BLOCKS
 #define LGCA_WAVE_MIN_BLOCKS 20
-#endif
-#ifndef LGCA_WAVE_MIN_BLOCKS_LOWK   // K <= 4 (A/B experiments: 24 = 80 registers)
-#define LGCA_WAVE_MIN_BLOCKS_LOWK LGCA_WAVE_MIN_BLOCKS
-#endif
-#ifndef LGCA_WAVE_CAP_NS            // 1: the no-slip wall variants carry the hint too (A/B experiments)
-#define LGCA_WAVE_CAP_NS 0
-#endif
-#ifndef LGCA_WAVE_CAP_KMAX          // deepest K that carries the hint
-#define LGCA_WAVE_CAP_KMAX 5
 #endif
 template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
 constexpr int wave_min_blocks()
 {
-    return (rule_of(MODEL) != MODEL_HPP && (!HAS_NS || LGCA_WAVE_CAP_NS) && !HAS_SL && !IRREG && K <= LGCA_WAVE_CAP_KMAX)
-               ? (K <= 4 ? LGCA_WAVE_MIN_BLOCKS_LOWK : LGCA_WAVE_MIN_BLOCKS) : 0; // 0 = no hint
+    return (rule_of(MODEL) != MODEL_HPP && !HAS_NS && !HAS_SL && !IRREG && K <= 5) ? LGCA_WAVE_MIN_BLOCKS : 0; // 0 = no hint
 }
 template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
 __global__ void __launch_bounds__(32, wave_min_blocks<MODEL, K, HAS_NS, HAS_SL, IRREG>()) step_wave_kernel(const WaveArgs A, const Geom g, const WavePlan wp)

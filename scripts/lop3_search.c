@@ -187,6 +187,20 @@ int main(int argc, char** argv)
         add_sig("a", n[0]); add_sig("b", n[3]); add_sig("tri", tri); add_sig("HO", HO); add_sig("p", p);
         add_sig("n1", n[1]); add_sig("n2", n[2]); add_sig("EE", EE); add_sig("EO", EO);
         add_target("o0", out[0]); add_target("o3", out[3]);
+    } else if (!strcmp(block, "pair1") || !strcmp(block, "pair2")) { // pair outputs with the T gate folded in [shipped: 1 + 4]
+        const int j = block[4] - '0';
+        tt nc = tt_and(tt_not(tri), tt_not(HO));
+        tt q  = tt_mux(tri, tt_not(n[0]), tt_xor(p, n[0]));
+        char b[8];
+        snprintf(b, 8, "n%d", j); add_sig(b, n[j]);
+        snprintf(b, 8, "n%d", j + 3); add_sig(b, n[j + 3]);
+        add_sig("nc", nc); add_sig("q", q); add_sig("EE", EE); add_sig("EO", EO);
+        snprintf(b, 8, "o%d", j); add_target(b, out[j]);
+        snprintf(b, 8, "o%d", j + 3); add_target(b, out[j + 3]);
+    } else if (!strcmp(block, "pair0")) { // pair (0,3) from tri, T1, T2 [shipped: 1 + 4]
+        add_sig("n0", n[0]); add_sig("n3", n[3]); add_sig("tri", tri); add_sig("T1", T[1]); add_sig("T2", T[2]);
+        add_sig("EE", EE); add_sig("EO", EO);
+        add_target("o0", out[0]); add_target("o3", out[3]);
     } else if (!strcmp(block, "rest")) { // everything after the T's: 6 movers + rest   [shipped: 4 + 12 + 1 = 17]
         for (int i = 0; i < 6; ++i) { char b[8]; snprintf(b, 8, "n%d", i); add_sig(b, n[i]); }
         add_sig("r", r); add_sig("se", se); add_sig("ce", ce); add_sig("so", so); add_sig("co", co);
