@@ -392,9 +392,14 @@ __global__ void __launch_bounds__(32, wave_min_blocks<MODEL, K, HAS_NS, HAS_SL, 
 }
 
 // Chunk height: enough tiles to fill the machine, long enough to amortise the K-row pipeline fill.
-// Cost model per fused step: every tile runs (cr + k - 1) level-rows (the fill is trapezoidal); tiles run
-// in rounds of `resident` warps per SM (from the occupancy of the kernel variant); an SM holding fewer
-// warps than that hides less latency and is modelled as sub-linearly slower.
+// Cost model per fused step (fitted to chunk-height sweeps on B200, profiles/r01b_chunk_sweep.md):
+//   * every tile runs (cr + k - 1) level-rows (the fill is trapezoidal) plus about three rows' worth of prologue;
+//   * tiles run in rounds of `resident` warps per SM (from the occupancy of the kernel variant); an SM holding fewer
+//     warps than that hides less latency and is modelled as sub-linearly slower;
+//   * the warp scheduler serves its resident warps by strict priority, so the warps of a round do NOT progress in
+//     lockstep: they finish staggered and the end of the launch runs with fewer and fewer warps per scheduler
+//     (ncu: 2.96 of 4 warps active on average for a one-round launch).  That tail costs about 0.15 of one round
+//     whatever the round is long, so two to four shorter rounds beat one long one (C5: -5.6 %, C4: -9 %).
 static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
 {
     const Geom& g = h->g;
@@ -412,7 +417,7 @@ static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
         const double w      = (double)chunks * wp.bands / 148.0; // warps per SM
         const double rounds = fmax(1.0, ceil(w / resident));
         const double eff    = pow(fmin(1.0, (w / rounds) / resident), 0.6);
-        const double cost   = (double)(cr + k - 1) * rounds / eff;
+        const double cost   = (double)(cr + k - 1 + 3) * (rounds + 0.15) / eff;
         if (cost <= best) { best = cost; best_cr = cr; }
     }
     int cr = best_cr;

@@ -1,0 +1,24 @@
+"""Chunk-height sweep of the fused-step kernel (development helper): LGCA_B200_CHUNK_ROWS is read when the plan is made."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import lgca_b200
+
+CASES = [("FHP_III", 32768, 32768, "periodic"), ("FHP_III", 16384, 8192, "karman"), ("FHP_II", 65536, 32768, "reflecting_back")]
+for model, dx, dy, bc in CASES:
+    for k in (6, 5):
+        for cr in (0, 1024, 700, 490, 410, 328, 246, 200, 164, 124, 100, 82):
+            if cr > dy:
+                continue
+            if cr:
+                os.environ["LGCA_B200_CHUNK_ROWS"] = str(cr)
+            else:
+                os.environ.pop("LGCA_B200_CHUNK_ROWS", None)
+            e = lgca_b200.Engine(model, dx, dy, k_fuse=k, flags=lgca_b200.capi.FLAG_NO_CELL_FIELDS)
+            e.apply_bc_device(bc)
+            e.init_random_device(1)
+            launches = max(4, int(2e-2 / (dx * dy * k / 8e12)))
+            e.timed_kernel(max(2, launches // 4))
+            ms = min(e.timed_kernel(launches) for _ in range(3))
+            print("%s %dx%d %s k=%d chunk_rows=%s: %.2f us/update  %.3e sites/s" % (
+                model, dx, dy, bc, k, cr or "planner", ms * 1e3 / k, dx * dy * k / (ms * 1e-3)), flush=True)
+            e.close()
