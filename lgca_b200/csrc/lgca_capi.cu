@@ -73,6 +73,23 @@ static inline size_t plane_words(const lgca_b200_lattice* h) { return (size_t)h-
 
 } // namespace lgca_b200
 
+namespace lgca_b200 {
+// Copy-on-write for the zero-copy snapshot: before the live buffer is modified in place (upload, init, body force,
+// halo import) the live state moves into the spare buffer and the snapshot keeps the old one.
+int unalias_snapshot(lgca_b200_lattice* h)
+{
+    if (!h->snap_spare) return 0;
+    SnapLock lock(h);
+    // the spare was the previous snapshot: the post stream may still be reading it
+    LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_post, 0));
+    LGCA_CUDA_CHECK(cudaMemcpyAsync(h->snap_spare, h->planes[h->cur], (size_t)h->g.plane_stride * sizeof(uint32_t) * h->nd,
+                                    cudaMemcpyDeviceToDevice, h->s_compute));
+    h->planes[h->cur] = h->snap_spare;
+    h->snap_spare = nullptr;
+    return 0;
+}
+} // namespace lgca_b200
+
 using namespace lgca_b200;
 
 extern "C" {
@@ -192,6 +209,7 @@ int lgca_b200_destroy(lgca_b200_lattice* h)
     cudaDeviceSynchronize();
     lgca_b200_ring_disconnect(h);
     cudaFree(h->ring_flags);
+    if (h->snap_spare) { h->planes[h->cur] = h->snap_spare; h->snap_spare = nullptr; } // undo the alias: free each buffer once
     for (int i = 0; i < 2; ++i) { cudaFree(h->planes[i]); cudaFree(h->d_stage[i]); }
     cudaFree(h->snap); cudaFree(h->ns); cudaFree(h->sl); cudaFree(h->ch); cudaFree(h->xedge); cudaFree(h->d_flags);
     cudaFree(h->d_cell_density); cudaFree(h->d_cell_momentum); cudaFree(h->d_mean_density); cudaFree(h->d_mean_momentum);
@@ -268,6 +286,7 @@ int lgca_b200_upload(lgca_b200_lattice* h, const uint8_t* state, const int32_t* 
         h->have_rnd = 1;
     }
     if (state) {
+        if ((rc = unalias_snapshot(h))) return rc; // in-place write: the snapshot must not see it
         // two-stage pipeline over the staging buffers: the copy engine (s_copy) moves chunk c+1 over PCIe while the
         // SMs (compute stream) transpose chunk c into bit-planes
         if ((rc = ensure_copy_stream(h))) return rc;
@@ -344,6 +363,10 @@ static int step_impl(lgca_b200_lattice* h, int n_steps, bool check_halo)
         else { k = 1; rc = launch_step_simple(h, in, out, h->s_compute); }
         if (rc) return rc;
         h->cur ^= 1;
+        if (h->snap_spare) { // `in` is the zero-copy snapshot: the retired snapshot buffer takes its slot in the pair
+            h->planes[h->cur ^ 1] = h->snap_spare;
+            h->snap_spare = nullptr;
+        }
         n_steps -= k;
     }
     return 0;
@@ -364,8 +387,16 @@ int lgca_b200_snapshot(lgca_b200_lattice* h)
         int rc = ring_wait_current_epoch(h);
         if (rc) return rc;
     }
-    LGCA_CUDA_CHECK(cudaMemcpyAsync(h->snap, h->planes[h->cur], plane_words(h) * sizeof(uint32_t) * h->nd,
-                                    cudaMemcpyDeviceToDevice, h->s_compute));
+    if (h->g.halo == 0 && !h->ring_connected) {
+        // zero-copy: the live buffer becomes the snapshot (see lgca_internal.h); nothing to do if it already is
+        if (!h->snap_spare) {
+            h->snap_spare = h->snap;
+            h->snap = h->planes[h->cur];
+        }
+    } else {
+        LGCA_CUDA_CHECK(cudaMemcpyAsync(h->snap, h->planes[h->cur], plane_words(h) * sizeof(uint32_t) * h->nd,
+                                        cudaMemcpyDeviceToDevice, h->s_compute));
+    }
     LGCA_CUDA_CHECK(cudaEventRecord(h->ev_snap, h->s_compute));
     return 0;
 }
@@ -498,6 +529,7 @@ int lgca_b200_body_force_apply(lgca_b200_lattice* h, const int32_t* cells, const
     memcpy(blob.data(), cells, n * 4);
     memcpy(blob.data() + n * 4, new_bytes, n);
     LGCA_CUDA_CHECK(cudaMemcpyAsync(h->d_draws, blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
+    if ((rc = unalias_snapshot(h))) return rc; // in-place write: the snapshot must not see it
     if ((rc = launch_apply_flips(h, h->planes[h->cur], h->d_draws, n, s))) return rc;
     LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
     return 0;
@@ -592,7 +624,8 @@ int lgca_b200_init_random_device(lgca_b200_lattice* h, uint64_t seed)
 {
     if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
-    int rc = launch_init_random(h, h->planes[h->cur], seed, h->s_compute);
+    int rc = unalias_snapshot(h);
+    if (!rc) rc = launch_init_random(h, h->planes[h->cur], seed, h->s_compute);
     if (rc) return rc;
     LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
     h->have_state = h->have_rnd = 1;

@@ -30,6 +30,12 @@ struct lgca_b200_lattice {
     uint32_t*        planes[2];   // ping-pong occupation planes [nd][rows][pitch]
     int              cur;         // index of the live buffer
     uint32_t*        snap;        // snapshot planes (copy_data_to_output_buffer)
+    // Whole lattices snapshot WITHOUT a copy: the live buffer itself becomes the snapshot (snap == planes[cur],
+    // `snap_spare` = the retired snapshot buffer).  The next step still reads it and writes the other buffer; after
+    // that step the spare takes the shared buffer's slot in the ping-pong pair.  Anything that writes the live buffer
+    // in place first calls unalias_snapshot() (copy-on-write).  Strips keep the copy: the ring neighbours hold fixed
+    // mappings of planes[0] / planes[1].
+    uint32_t*        snap_spare;
     uint32_t*        ns;          // no-slip solid mask plane  [rows][pitch]
     uint32_t*        sl;          // slip solid mask plane
     uint32_t*        ch;          // chirality plane
@@ -97,7 +103,8 @@ bool wave_supported(const lgca_b200_lattice* h, int k);
 int wave_prepare(lgca_b200_lattice* h);
 bool wave_has_edge_chunks(lgca_b200_lattice* h, int k);
 int simple_prepare(lgca_b200_lattice* h);
-int ring_wait_current_epoch(lgca_b200_lattice* h); // lgca_ring.cu: stream-ordered wait for the neighbours' latest pushes
+int ring_wait_current_epoch(lgca_b200_lattice* h);
+int unalias_snapshot(lgca_b200_lattice* h); // lgca_capi.cu: give the live state a buffer of its own before an in-place write // lgca_ring.cu: stream-ordered wait for the neighbours' latest pushes
 
 // lgca_pack.cu : reference layouts <-> bit-planes
 int launch_pack_state(lgca_b200_lattice* h, const uint8_t* d_bytes, uint32_t* planes, uint32_t row0, uint32_t nrows,

@@ -329,3 +329,49 @@ def test_full_size_karman_parity_and_conservation():
     assert np.array_equal(e2.download(), e3.download())
     for x in (e, e2, e3):
         x.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("writer", ["step1", "step2", "body_force", "upload", "init", "none"])
+def test_snapshot_is_insulated_from_every_writer(writer):
+    """copy_data_to_output_buffer (src/lattice.cpp:437-441) freezes the state.  Whole lattices snapshot without a copy
+    (the live buffer becomes the snapshot, copy-on-write for in-place writers): whatever touches the live state
+    afterwards, post_process must still see the state of the snapshot, and the live state must be the oracle's."""
+    o = Oracle("FHP_III", dims=(192, 64), cg=4, bf_dir=b"x", rng=OracleRng(5))
+    o.apply_bc("pipe")
+    o.init("random")
+    e = engine_from(o)
+    e.step(4)
+    o.step(4)
+    e.snapshot()
+    e.snapshot()           # twice in a row: still the same state
+    o.snapshot()
+    o.post_process()
+    if writer == "step1":
+        e.step(1); o.step(1)
+    elif writer == "step2":
+        e.step(1); e.step(1); e.step(5); o.step(7)
+    elif writer == "body_force":
+        o.rng = OracleRng(77)
+        used_o, rev_o = o.body_force(25)
+        rng = OracleRng(77)
+        draws = np.array([rng.rand() for _ in range(used_o + 10)], np.int32)
+        assert e.body_force(25, draws) == (used_o, rev_o)
+    elif writer == "upload":
+        o.step(3)
+        e.upload(state=o.state)
+    elif writer == "init":
+        e.init_random_device(9)
+    f = e.post_process(cell=True, mean=True, exact=True)
+    assert np.array_equal(f["cell_density"], o.cell_density)
+    assert np.array_equal(f["cell_momentum"], o.cell_momentum)
+    assert np.array_equal(f["mean_density"], o.mean_density)
+    if writer != "init":
+        assert np.array_equal(e.download(), o.state)
+        # and the next snapshot follows the live state again
+        e.step(2); o.step(2)
+        e.snapshot(); o.snapshot(); o.post_process()
+        f = e.post_process(cell=True, mean=False, exact=True)
+        assert np.array_equal(f["cell_density"], o.cell_density)
+        assert np.array_equal(e.download(), o.state)
+    e.close()
