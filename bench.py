@@ -263,7 +263,9 @@ def run_b200_arm(args):
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
-        # keep stdout to the one JSON line (the image sets NCCL_DEBUG=VERSION, which prints a banner there)
+        # keep stdout to the one JSON line: NCCL writes its debug output (the image sets NCCL_DEBUG=VERSION, and the
+        # version banner is printed at WARN level too) to stdout unless told otherwise
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
