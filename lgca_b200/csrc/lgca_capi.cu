@@ -219,6 +219,7 @@ int lgca_b200_destroy(lgca_b200_lattice* h)
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_post) cudaStreamDestroy(h->s_post);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
+    for (int k = 0; k <= LGCA_MAX_K; ++k) cudaFree(h->tile_fluid[k]);
     if (h->snap_mutex_init) pthread_mutex_destroy(&h->snap_mutex);
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
     if (h->ev_post) cudaEventDestroy(h->ev_post);
@@ -776,6 +777,7 @@ int lgca_b200_halo_import(lgca_b200_lattice* h, int what, const void* dev_from_u
     // the upper neighbour's bottom rows fill the halo above the strip, and vice versa
     int rc = halo_copy(h, what, const_cast<void*>(dev_from_upper), g.rows - g.halo, false);
     if (!rc) rc = halo_copy(h, what, const_cast<void*>(dev_from_lower), 0, false);
+    if (what == LGCA_B200_HALO_MASKS) memset(h->plan_valid, 0, sizeof(h->plan_valid)); // ghost-row masks changed: per-tile flags are stale
     return rc;
 }
 

@@ -68,6 +68,8 @@ struct lgca_b200_lattice {
     size_t           draw_cap;
     lgca_b200::WavePlan plans[LGCA_MAX_K + 1];
     int              plan_valid[LGCA_MAX_K + 1];
+    uint8_t*         tile_fluid[LGCA_MAX_K + 1];      // per plan: 1 = tile window holds no solid site (wall variants)
+    size_t           tile_fluid_cap[LGCA_MAX_K + 1];
     uint64_t         launches;
     uint64_t         device_bytes;
     // native halo ring (lgca_ring.cu)

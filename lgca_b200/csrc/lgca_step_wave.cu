@@ -70,6 +70,7 @@ struct WaveArgs {
     // native ring: tiles that read ghost rows spin until the neighbours have published `ring_epoch`
     const uint32_t* ring_flags; // [0] from the lower neighbour, [1] from the upper; nullptr = no in-kernel wait
     uint32_t        ring_epoch;
+    const uint8_t*  tile_fluid;        // wall variants: [chunks * bands] 1 = the tile's input window is all fluid (or nullptr)
     uint32_t        stride_bytes;      // distance between consecutive planes of a set (in[d] = in[0] + d * stride)
     uint32_t        mul_two, mul_half; // 2 and 2^31: run-time multipliers of the FMA-pipe funnel shifts (up1/down1)
 };
@@ -270,22 +271,12 @@ constexpr int wave_min_blocks()
 {
     return (rule_of(MODEL) != MODEL_HPP && !HAS_NS && !HAS_SL && !IRREG && K <= 5) ? LGCA_WAVE_MIN_BLOCKS : 0; // 0 = no hint
 }
-template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
-__global__ void __launch_bounds__(32, wave_min_blocks<MODEL, K, HAS_NS, HAS_SL, IRREG>()) step_wave_kernel(const WaveArgs A, const Geom g, const WavePlan wp)
+// Row range [oa, ob) of a tile's output, relative to the first owned row.  Whole lattices: uniform chunks.
+// Strips: tile rows 0 and 1 are the bottom and the top EDGE chunk (the only ones that read ghost rows); they are
+// scheduled first and are shorter than the interior chunks, so that waiting for the neighbours' ghost rows at
+// their start does not delay the end of the kernel.
+__device__ __forceinline__ void tile_rows(const Geom& g, const WavePlan& wp, int c, int& oa, int& ob)
 {
-    constexpr int ND = num_dir_of(MODEL);
-    const int lane = threadIdx.x;
-    // one warp per block: the tile index (and with it every loop bound) is provably warp-uniform, so the
-    // shuffles in the row loop compile to plain SHFL without convergence bookkeeping
-    // 2-D grid (x = band, y = chunk; blocks are issued x-fastest, so the chunk order is the schedule order): no
-    // division, so every row index below stays on the uniform datapath
-    const int band = blockIdx.x;
-    const int c    = blockIdx.y;
-    // Row range [ya, yb) of this tile's output, relative to the first owned row.  Whole lattices: uniform chunks.
-    // Strips: tile rows 0 and 1 are the bottom and the top EDGE chunk (the only ones that read ghost rows); they are
-    // scheduled first and are shorter than the interior chunks, so that waiting for the neighbours' ghost rows at
-    // their start does not delay the end of the kernel.
-    int oa, ob;
     const int owned = (int)(g.rows - 2 * g.halo);
     if (wp.edge_rows == 0) {
         oa = c * wp.chunk_rows;
@@ -298,6 +289,44 @@ __global__ void __launch_bounds__(32, wave_min_blocks<MODEL, K, HAS_NS, HAS_SL, 
         oa = wp.edge_rows + (c - 2) * wp.chunk_rows;
         ob = min(oa + wp.chunk_rows, owned - wp.edge_rows);
     }
+}
+
+// Periodic images in x are resolved ONCE per lane:
+//   * width a multiple of 32: every lane reads one plain word at a wrapped index;
+//   * otherwise lanes whose 32 sites touch the row end assemble them from up to three words
+//     (two around bit position p, plus word 0 after the wrap) with precomputed indices/shifts.
+template <bool IRREG>
+__device__ __forceinline__ LaneSrc<IRREG> make_lane_src(const Geom& g, int wi)
+{
+    LaneSrc<IRREG> src;
+    src.wb = 0; src.sh = 0; src.n1 = 32; src.regular = true;
+    int wa = wi;
+    if (!IRREG) {
+        if (wa < 0) wa += (int)g.nw;
+        else if (wa >= (int)g.nw) wa %= (int)g.nw;
+    } else {
+        src.regular = (wi >= 0) && (wi < (int)g.nw - 1);
+        if (!src.regular) {
+            long long p = ((long long)wi * 32) % (long long)g.dim_x;
+            if (p < 0) p += g.dim_x;
+            wa      = (int)(p >> 5);
+            src.sh  = (int)(p & 31);
+            src.wb  = (uint32_t)min(wa + 1, (int)g.nw - 1);
+            src.n1  = (int)min((long long)32, (long long)g.dim_x - p); // sites before the row end
+        }
+    }
+    src.wa = (uint32_t)wa;
+    return src;
+}
+
+// One tile (band x chunk) of the fused-step kernel.
+template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
+__device__ __forceinline__ void wave_tile(const WaveArgs& A, const Geom& g, const WavePlan& wp, const int band, const int c)
+{
+    constexpr int ND = num_dir_of(MODEL);
+    const int lane = threadIdx.x;
+    int oa, ob;
+    tile_rows(g, wp, c, oa, ob);
     if (wp.edge_rows && A.ring_flags && c < 2) {
         // in-kernel halo wait: only the edge tiles depend on the neighbours' pushes; everyone else starts at once
         if (lane == 0) {
@@ -314,30 +343,7 @@ __global__ void __launch_bounds__(32, wave_min_blocks<MODEL, K, HAS_NS, HAS_SL, 
     const int total = (yb - ya) + 2 * K;                     // level-0 rows to push through
     const int rows  = (int)g.rows;
 
-    // Periodic images in x are resolved ONCE per lane:
-    //   * width a multiple of 32: every lane reads one plain word at a wrapped index;
-    //   * otherwise lanes whose 32 sites touch the row end assemble them from up to three words
-    //     (two around bit position p, plus word 0 after the wrap) with precomputed indices/shifts.
-    LaneSrc<IRREG> src;
-    src.wb = 0; src.sh = 0; src.n1 = 32; src.regular = true;
-    {
-        int wa = wi;
-        if (!IRREG) {
-            if (wa < 0) wa += (int)g.nw;
-            else if (wa >= (int)g.nw) wa %= (int)g.nw;
-        } else {
-            src.regular = (wi >= 0) && (wi < (int)g.nw - 1);
-            if (!src.regular) {
-                long long p = ((long long)wi * 32) % (long long)g.dim_x;
-                if (p < 0) p += g.dim_x;
-                wa      = (int)(p >> 5);
-                src.sh  = (int)(p & 31);
-                src.wb  = (uint32_t)min(wa + 1, (int)g.nw - 1);
-                src.n1  = (int)min((long long)32, (long long)g.dim_x - p); // sites before the row end
-            }
-        }
-        src.wa = (uint32_t)wa;
-    }
+    const LaneSrc<IRREG> src = make_lane_src<IRREG>(g, wi);
     const bool     store_lane = (lane >= 1) && (lane <= WAVE_VALID) && (wi < (int)g.nw);
     const uint32_t vmask      = store_lane ? valid_mask(g, wi) : 0u;
     const uint32_t ew         = HAS_SL ? src.load(A.xedge, 0u) : 0u;
@@ -389,6 +395,50 @@ __global__ void __launch_bounds__(32, wave_min_blocks<MODEL, K, HAS_NS, HAS_SL, 
     }
     if (j < total) LGCA_ROW(0, false, j); // odd number of rows (HPP lattices with odd height)
 #undef LGCA_ROW
+}
+
+// The kernel: one warp per block (the tile index and with it every loop bound is provably warp-uniform, so the
+// shuffles in the row loop compile to plain SHFL without convergence bookkeeping); 2-D grid (x = band, y = chunk;
+// blocks are issued x-fastest, so the chunk order is the schedule order) without a division, so every row index stays
+// on the uniform datapath.
+// Wall variants: walls are rare (C3: two wall rows and a cylinder, C4: a frame).  A tile whose input window -- its
+// rows incl. the K-row aprons, its 32 word columns incl. the halo lanes -- holds no solid site at all runs the
+// ALL-FLUID tile body (no mask loads, no pre-collision copies, no votes, no wall muxes, no mask delay lines); the
+// per-tile flags are computed once per plan by tile_fluid_kernel.  The choice is per block, so the two bodies never
+// merge inside a loop.
+template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
+__global__ void __launch_bounds__(32, wave_min_blocks<MODEL, K, HAS_NS, HAS_SL, IRREG>()) step_wave_kernel(const WaveArgs A, const Geom g, const WavePlan wp)
+{
+    const int band = blockIdx.x;
+    const int c    = blockIdx.y;
+    if ((HAS_NS || HAS_SL) && A.tile_fluid != nullptr && A.tile_fluid[c * wp.bands + band] != 0)
+        wave_tile<MODEL, K, false, false, IRREG>(A, g, wp, band, c);
+    else
+        wave_tile<MODEL, K, HAS_NS, HAS_SL, IRREG>(A, g, wp, band, c);
+}
+
+// tile_fluid[c * bands + band] = 1 when no solid site lies in the tile's input window (same geometry as wave_tile).
+template <bool IRREG>
+__global__ void __launch_bounds__(32) tile_fluid_kernel(const uint32_t* __restrict__ ns, const uint32_t* __restrict__ sl,
+                                                        const Geom g, const WavePlan wp, const int K, uint8_t* __restrict__ out)
+{
+    const int band = blockIdx.x, c = blockIdx.y, lane = threadIdx.x;
+    int oa, ob;
+    tile_rows(g, wp, c, oa, ob);
+    const int wi   = band * WAVE_VALID - 1 + lane;
+    const int rows = (int)g.rows;
+    const LaneSrc<IRREG> src = make_lane_src<IRREG>(g, wi);
+    const int total = (ob - oa) + 2 * K;
+    int r = (int)g.halo + oa - K;
+    if (r < 0) r += rows;
+    uint32_t acc = 0u;
+    for (int j = 0; j < total; ++j) {
+        const uint32_t ro = (uint32_t)r * g.pitch;
+        acc |= src.load(ns, ro) | src.load(sl, ro);
+        if (++r >= rows) r -= rows;
+    }
+    const bool solid = __any_sync(0xFFFFFFFFu, acc != 0u);
+    if (lane == 0) out[c * wp.bands + band] = solid ? 0 : 1;
 }
 
 // Chunk height: enough tiles to fill the machine, long enough to amortise the K-row pipeline fill.
@@ -462,6 +512,22 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
         int blocks = 0;
         LGCA_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks, kernel, 32, 0));
         h->plans[K] = make_plan(h, K, blocks > 0 ? blocks : 16);
+        if (NS || SL) {
+            // per-tile "all fluid" flags of this plan (the masks are static; every mask writer invalidates the plans)
+            const WavePlan& p = h->plans[K];
+            const size_t need = (size_t)p.tiles;
+            if (h->tile_fluid_cap[K] < need) {
+                if (h->tile_fluid[K]) cudaFree(h->tile_fluid[K]);
+                h->tile_fluid[K] = nullptr; h->tile_fluid_cap[K] = 0;
+                LGCA_CUDA_CHECK(cudaMalloc((void**)&h->tile_fluid[K], need));
+                h->tile_fluid_cap[K] = need;
+            }
+            if (p.chunks > 65535) return set_error(LGCA_B200_EINVAL, "chunk plan exceeds gridDim.y (%d chunks)", p.chunks);
+            tile_fluid_kernel<IRREG><<<dim3(p.bands, p.chunks, 1), dim3(32, 1, 1), 0, h->s_compute>>>(h->ns, h->sl, h->g, p, K,
+                                                                                              h->tile_fluid[K]);
+            h->launches++;
+            LGCA_CUDA_CHECK(cudaGetLastError());
+        }
         h->plan_valid[K] = 1;
     }
     const WavePlan wp = h->plans[K];
@@ -476,6 +542,7 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
     A.ring_epoch = h->ring_inkernel_epoch;
     A.mul_two = 2u; A.mul_half = 0x80000000u;
     A.stride_bytes = (uint32_t)(h->g.plane_stride * sizeof(uint32_t));
+    A.tile_fluid = (NS || SL) ? h->tile_fluid[K] : nullptr;
     if (!in) return 0; // prepare only (wave_prepare): plan + module load, no launch
     if (wp.chunks > 65535) return set_error(LGCA_B200_EINVAL, "chunk plan exceeds gridDim.y (%d chunks)", wp.chunks);
     kernel<<<dim3(wp.bands, wp.chunks, 1), dim3(32, 1, 1), 0, s>>>(A, h->g, wp);

@@ -4,9 +4,15 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lgca_b200
 
 CASES = [("FHP_III", 32768, 32768, "periodic"), ("FHP_III", 16384, 8192, "karman"), ("FHP_II", 65536, 32768, "reflecting_back")]
+CHUNKS = (0, 1024, 700, 490, 410, 328, 246, 200, 164, 124, 100, 82)
+KS = (6, 5)
+if len(sys.argv) > 1:  # e.g. chunk_sweep.py karman 6 0,32,48,64,96
+    CASES = [c for c in CASES if c[3] == sys.argv[1]]
+    KS = tuple(int(x) for x in sys.argv[2].split(","))
+    CHUNKS = tuple(int(x) for x in sys.argv[3].split(","))
 for model, dx, dy, bc in CASES:
-    for k in (6, 5):
-        for cr in (0, 1024, 700, 490, 410, 328, 246, 200, 164, 124, 100, 82):
+    for k in KS:
+        for cr in CHUNKS:
             if cr > dy:
                 continue
             if cr:
