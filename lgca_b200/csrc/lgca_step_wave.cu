@@ -601,6 +601,10 @@ bool wave_has_edge_chunks(lgca_b200_lattice* h, int k)
 // same process is spinning in the ring's wait kernel; the ring calls this before it starts.
 int wave_prepare(lgca_b200_lattice* h)
 {
+    // the flag kernel too: a plan may be re-made (mask upload) after the ring has started
+    cudaFuncAttributes fa;
+    LGCA_CUDA_CHECK(cudaFuncGetAttributes(&fa, tile_fluid_kernel<false>));
+    LGCA_CUDA_CHECK(cudaFuncGetAttributes(&fa, tile_fluid_kernel<true>));
     for (int k = 1; k <= h->k_fuse; ++k) {
         if (!wave_supported(h, k)) continue;
         const int rc = launch_step_wave(h, nullptr, nullptr, k, 0);
