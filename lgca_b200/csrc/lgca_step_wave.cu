@@ -16,9 +16,15 @@
 //     K <= 32 the 30 interior words stay exact.  Chunks overlap by K rows at both ends (recomputed).
 //   * Periodic wrap: rows by index arithmetic; in x the edge lanes read the periodic image of their
 //     word (resolved once per lane), which also covers widths that are not multiples of 32.
-//   * The next level-0 row and the level-1 masks are prefetched one iteration ahead; the pipeline
+//   * Level-0 rows are prefetched two iterations ahead, the level-1 masks one; the pipeline
 //     fill (first 2K rows of a chunk) runs in a separate, predicated copy of the row body so that the
 //     steady-state loop is branch-free.
+//   * One warp per block on a 2-D grid (band, chunk): every row index and loop bound is warp-uniform and lives
+//     on the uniform datapath; plane addresses are one IMAD.WIDE each (row pointer + plane stride * d).
+//   * Wall variants dispatch, per tile, to the all-fluid tile body when the tile's whole input window holds no
+//     solid site (flag map computed once per plan by tile_fluid_kernel).
+//   * Tiling (make_plan): 2-4 rounds of resident warps per launch -- the scheduler serves its warps by strict
+//     priority, so one long round ends with half-empty schedulers.
 #include <math.h>
 #include <stdlib.h>
 
