@@ -102,7 +102,10 @@ int  lgca_b200_download(lgca_b200_lattice* h, uint8_t* state);
  * (the chirality comes from the frozen rnd bit-field). */
 int  lgca_b200_step(lgca_b200_lattice* h, int n_steps);
 
-/* ---- Lattice::copy_data_to_output_buffer(), src/lattice.h:211 / src/lattice.cpp:437-441 ---- */
+/* ---- Lattice::copy_data_to_output_buffer(), src/lattice.h:211 / src/lattice.cpp:437-441 ----
+ * Freezes the live state for post-processing.  No copy is made: the handle rotates three plane sets (the live set
+ * becomes the snapshot, the next step writes a fresh set; in-place writers copy on write).  Row strips rotate in
+ * lockstep, so all strips of a lattice must issue the same sequence of step / snapshot / in-place-write calls. */
 int  lgca_b200_snapshot(lgca_b200_lattice* h);
 
 /* ---- Lattice::post_process(), src/lattice.h:203 / src/omp_lattice.cpp:349-454 ----
@@ -185,6 +188,10 @@ int  lgca_b200_get_info(lgca_b200_lattice* h, lgca_b200_info* out);
  * slip, chirality), which are exchanged once after an upload from the host. */
 enum { LGCA_B200_HALO_STATE = 0, LGCA_B200_HALO_MASKS = 1 };
 int  lgca_b200_halo_rows(lgca_b200_lattice* h, uint32_t* rows);
+/* Steps a strip may advance between two halo exchanges = steps ONE kernel launch can take: the fused depth of the
+ * wavefront kernel, or 1 where only the generic kernel applies (dim_x < 64, fewer than 8 stored rows,
+ * LGCA_B200_FLAG_SIMPLE_KERNEL).  lgca_b200_step rejects more than this on a strip (LGCA_B200_ESTATE). */
+int  lgca_b200_steps_per_exchange(lgca_b200_lattice* h, int* steps);
 int  lgca_b200_halo_bytes(lgca_b200_lattice* h, int what, size_t* bytes_per_side);
 int  lgca_b200_halo_export(lgca_b200_lattice* h, int what, void* dev_top_rows, void* dev_bottom_rows);
 int  lgca_b200_halo_import(lgca_b200_lattice* h, int what, const void* dev_from_upper, const void* dev_from_lower);
@@ -205,7 +212,46 @@ int  lgca_b200_ring_export(lgca_b200_lattice* h, void* descriptor, size_t bytes)
 int  lgca_b200_ring_connect(lgca_b200_lattice* h, const void* lower_descriptor, const void* upper_descriptor);
 int  lgca_b200_ring_start(lgca_b200_lattice* h);
 int  lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps);
+/* Publishes the edge rows again WITHOUT a step in between: mandatory (on every strip, at the same point of the
+ * call sequence) after anything that changed the live state in place while the ring is running -- the body force
+ * (lgca_b200_body_force_apply), a new upload, an initialiser.  Stream-ordered; neighbours acknowledge that they no
+ * longer read the ghost rows being replaced before the new rows are stored. */
+int  lgca_b200_ring_republish(lgca_b200_lattice* h);
 int  lgca_b200_ring_disconnect(lgca_b200_lattice* h);
+
+/* ---- one lattice on several GPUs of one box, driven by ONE host process ----------------------------------------
+ * The handle the C++ backend B200_Lattice<Model> talks to (reference boundary: the Lattice<Model> virtuals,
+ * src/lattice.h:187-211; an app picks the backend where it says `new OMP_Lattice<MODEL>(...)`,
+ * apps/pipe/pipe_viewer.cpp:46, or with the stale CLI's -p switch, apps/periodic/main.cpp:78-96).  A group owns
+ * n_gpus row strips (contiguous, heights multiples of 2*cg_radius, even), one per device, connected by the native
+ * halo ring through same-process peer pointers.  All host arrays are GLOBAL reference-layout arrays of the whole
+ * lattice (see the top of this file); results are identical to a single-GPU handle (decomposition invariance).
+ * n_gpus == 1 is a plain whole-lattice handle.  `dev_ids` NULL = devices 0 .. n_gpus-1; cfg->device, y_begin and
+ * y_rows are ignored.  Same status codes and threading rules as the single-handle calls. */
+typedef struct lgca_b200_group lgca_b200_group; /* opaque */
+int  lgca_b200_group_create(const lgca_b200_config* cfg, int n_gpus, const int* dev_ids, lgca_b200_group** out);
+int  lgca_b200_group_destroy(lgca_b200_group* g);
+int  lgca_b200_group_size(lgca_b200_group* g, int* n_gpus);
+/* borrowed pointer to strip i's handle (introspection, tests) */
+int  lgca_b200_group_strip(lgca_b200_group* g, int i, lgca_b200_lattice** h);
+int  lgca_b200_group_upload(lgca_b200_group* g, const uint8_t* state, const int32_t* cell_type, const uint8_t* rnd_bits);
+int  lgca_b200_group_download(lgca_b200_group* g, uint8_t* state);
+int  lgca_b200_group_step(lgca_b200_group* g, int n_steps);
+int  lgca_b200_group_snapshot(lgca_b200_group* g);
+int  lgca_b200_group_post_process(lgca_b200_group* g, float* cell_density, float* cell_momentum, float* mean_density,
+                                  float* mean_momentum, int exact_order);
+int  lgca_b200_group_mean_velocity(lgca_b200_group* g, float out[2]);
+int  lgca_b200_group_body_force(lgca_b200_group* g, int forcing, const int32_t* draws, size_t n_draws, size_t* consumed,
+                                uint32_t* reverted);
+int  lgca_b200_group_count_particles(lgca_b200_group* g, uint64_t* out);
+int  lgca_b200_group_init_random_device(lgca_b200_group* g, uint64_t seed);
+int  lgca_b200_group_apply_bc_device(lgca_b200_group* g, const char* bc);
+int  lgca_b200_group_sync(lgca_b200_group* g);
+/* n_steps updates bracketed by CUDA events on every strip's compute stream; elapsed = max over the strips */
+int  lgca_b200_group_timed_steps(lgca_b200_group* g, int n_steps, float* elapsed_ms);
+int  lgca_b200_group_launch_count(lgca_b200_group* g, uint64_t* out);
+/* global dims; y_rows = dim_y; device_bytes summed over the strips; k_fuse = steps per halo exchange */
+int  lgca_b200_group_get_info(lgca_b200_group* g, lgca_b200_info* out);
 
 #ifdef __cplusplus
 }

@@ -4,6 +4,6 @@ The product is ``liblgca_b200.so`` (sources in ``lgca_b200/csrc``, C-ABI in ``in
 C++ ``B200_Lattice<Model>`` host class in ``lgca_b200/host``.  This Python package is only the thin ctypes
 binding used by the tests and ``bench.py``; it never computes anything itself and has no CPU fallback.
 """
-from .capi import Engine, LgcaError, MODELS, library_path, load_library  # noqa: F401
+from .capi import Engine, Group, LgcaError, MODELS, library_path, load_library  # noqa: F401
 
-__all__ = ["Engine", "LgcaError", "MODELS", "library_path", "load_library"]
+__all__ = ["Engine", "Group", "LgcaError", "MODELS", "library_path", "load_library"]

@@ -24,7 +24,12 @@ SYMBOLS = [
     "lgca_b200_halo_rows", "lgca_b200_halo_bytes", "lgca_b200_halo_export", "lgca_b200_halo_import",
     "lgca_b200_get_wall_flags", "lgca_b200_set_wall_flags",
     "lgca_b200_ring_descriptor_bytes", "lgca_b200_ring_export", "lgca_b200_ring_connect", "lgca_b200_ring_start",
-    "lgca_b200_ring_step", "lgca_b200_ring_disconnect",
+    "lgca_b200_ring_step", "lgca_b200_ring_disconnect", "lgca_b200_ring_republish", "lgca_b200_steps_per_exchange",
+    "lgca_b200_group_create", "lgca_b200_group_destroy", "lgca_b200_group_size", "lgca_b200_group_strip",
+    "lgca_b200_group_upload", "lgca_b200_group_download", "lgca_b200_group_step", "lgca_b200_group_snapshot",
+    "lgca_b200_group_post_process", "lgca_b200_group_mean_velocity", "lgca_b200_group_body_force",
+    "lgca_b200_group_count_particles", "lgca_b200_group_init_random_device", "lgca_b200_group_apply_bc_device",
+    "lgca_b200_group_sync", "lgca_b200_group_timed_steps", "lgca_b200_group_launch_count", "lgca_b200_group_get_info",
 ]
 
 
@@ -102,6 +107,26 @@ def load_library():
     L.lgca_b200_ring_start.argtypes = [vp]
     L.lgca_b200_ring_step.argtypes = [vp, i32]
     L.lgca_b200_ring_disconnect.argtypes = [vp]
+    L.lgca_b200_ring_republish.argtypes = [vp]
+    L.lgca_b200_steps_per_exchange.argtypes = [vp, C.POINTER(C.c_int)]
+    L.lgca_b200_group_create.argtypes = [C.POINTER(Config), i32, vp, C.POINTER(vp)]
+    L.lgca_b200_group_destroy.argtypes = [vp]
+    L.lgca_b200_group_size.argtypes = [vp, C.POINTER(C.c_int)]
+    L.lgca_b200_group_strip.argtypes = [vp, i32, C.POINTER(vp)]
+    L.lgca_b200_group_upload.argtypes = [vp, vp, vp, vp]
+    L.lgca_b200_group_download.argtypes = [vp, vp]
+    L.lgca_b200_group_step.argtypes = [vp, i32]
+    L.lgca_b200_group_snapshot.argtypes = [vp]
+    L.lgca_b200_group_post_process.argtypes = [vp, vp, vp, vp, vp, i32]
+    L.lgca_b200_group_mean_velocity.argtypes = [vp, vp]
+    L.lgca_b200_group_body_force.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
+    L.lgca_b200_group_count_particles.argtypes = [vp, C.POINTER(u64)]
+    L.lgca_b200_group_init_random_device.argtypes = [vp, u64]
+    L.lgca_b200_group_apply_bc_device.argtypes = [vp, C.c_char_p]
+    L.lgca_b200_group_sync.argtypes = [vp]
+    L.lgca_b200_group_timed_steps.argtypes = [vp, i32, C.POINTER(C.c_float)]
+    L.lgca_b200_group_launch_count.argtypes = [vp, C.POINTER(u64)]
+    L.lgca_b200_group_get_info.argtypes = [vp, C.POINTER(Info)]
     _LIB = L
     return L
 
@@ -293,9 +318,10 @@ class Engine:
         return int(v.value)
 
     def steps_per_exchange(self):
-        """Steps a strip may advance between two halo exchanges (one launch of the fused-step kernel)."""
-        i = self.info()
-        return 1 if (self._flags & FLAG_SIMPLE_KERNEL) else max(1, min(int(i.k_fuse), self.halo_rows()))
+        """Steps a strip may advance between two halo exchanges (one launch of the kernel that will actually run)."""
+        v = C.c_int(0)
+        self._check(self.L.lgca_b200_steps_per_exchange(self.h, C.byref(v)))
+        return int(v.value)
 
     def halo_bytes(self, what=0):
         v = C.c_size_t(0)
@@ -330,6 +356,9 @@ class Engine:
     def ring_disconnect(self):
         self._check(self.L.lgca_b200_ring_disconnect(self.h))
 
+    def ring_republish(self):
+        self._check(self.L.lgca_b200_ring_republish(self.h))
+
     def wall_flags(self):
         a, b = C.c_uint32(0), C.c_uint32(0)
         self._check(self.L.lgca_b200_get_wall_flags(self.h, C.byref(a), C.byref(b)))
@@ -337,3 +366,117 @@ class Engine:
 
     def set_wall_flags(self, has_no_slip, has_slip):
         self._check(self.L.lgca_b200_set_wall_flags(self.h, int(has_no_slip), int(has_slip)))
+
+
+class Group:
+    """One lattice on n GPUs of this box driven by ONE process (lgca_b200_group_*): same calls as Engine, all host
+    arrays are GLOBAL reference-layout arrays.  n_gpus == 1 is a plain whole-lattice handle."""
+
+    def __init__(self, model, dim_x, dim_y, n_gpus=1, dev_ids=None, cg_radius=0, bf_dir=0, k_fuse=0, flags=0):
+        self.L = load_library()
+        self.model = MODELS[model] if isinstance(model, str) else int(model)
+        if isinstance(bf_dir, (bytes, str)):
+            bf_dir = ord(bf_dir) if bf_dir not in (b"\0", "\0", "", b"") else 0
+        cfg = Config(self.model, dim_x, dim_y, cg_radius, bf_dir, 0, k_fuse, 0, 0, flags)
+        ids = None
+        if dev_ids is not None:
+            ids = (C.c_int * n_gpus)(*dev_ids)
+        g = C.c_void_p()
+        self._check(self.L.lgca_b200_group_create(C.byref(cfg), int(n_gpus), ids, C.byref(g)))
+        self.g = g
+        self.n_gpus = int(n_gpus)
+        self.dim_x, self.dim_y, self.cg = dim_x, dim_y, cg_radius
+        self.cells = dim_x * dim_y
+        self.num_dir = NUM_DIR[self.model]
+
+    _check = Engine._check
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.L.lgca_b200_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload(self, state=None, cell_type=None, rnd_bits=None):
+        if state is not None:
+            state = np.ascontiguousarray(state, np.uint8)
+            assert state.size == self.cells
+        if cell_type is not None:
+            cell_type = np.ascontiguousarray(cell_type, np.int32)
+            assert cell_type.size == self.cells
+        if rnd_bits is not None:
+            rnd_bits = np.ascontiguousarray(rnd_bits, np.uint8)
+            assert rnd_bits.size >= (self.cells + 7) // 8
+        self._check(self.L.lgca_b200_group_upload(self.g, _ptr(state), _ptr(cell_type), _ptr(rnd_bits)))
+
+    def download(self, out=None):
+        if out is None:
+            out = np.empty(self.cells, np.uint8)
+        self._check(self.L.lgca_b200_group_download(self.g, _ptr(out)))
+        return out
+
+    def step(self, n=1):
+        self._check(self.L.lgca_b200_group_step(self.g, int(n)))
+
+    def timed_steps(self, n):
+        ms = C.c_float(0)
+        self._check(self.L.lgca_b200_group_timed_steps(self.g, int(n), C.byref(ms)))
+        return float(ms.value)
+
+    def sync(self):
+        self._check(self.L.lgca_b200_group_sync(self.g))
+
+    def snapshot(self):
+        self._check(self.L.lgca_b200_group_snapshot(self.g))
+
+    def post_process(self, cell=True, mean=True, exact=True, out=None):
+        out = {} if out is None else out
+        n = self.cells
+        if cell:
+            out.setdefault("cell_density", np.empty(n, np.float32))
+            out.setdefault("cell_momentum", np.empty(2 * n, np.float32))
+        if mean:
+            nc = (self.dim_x // (2 * self.cg)) * (self.dim_y // (2 * self.cg))
+            out.setdefault("mean_density", np.empty(nc, np.float32))
+            out.setdefault("mean_momentum", np.empty(2 * nc, np.float32))
+        self._check(self.L.lgca_b200_group_post_process(self.g, _ptr(out.get("cell_density")), _ptr(out.get("cell_momentum")),
+                                                        _ptr(out.get("mean_density")), _ptr(out.get("mean_momentum")),
+                                                        1 if exact else 0))
+        return out
+
+    def mean_velocity(self):
+        out = np.zeros(2, np.float32)
+        self._check(self.L.lgca_b200_group_mean_velocity(self.g, _ptr(out)))
+        return out
+
+    def body_force(self, forcing, draws):
+        draws = np.ascontiguousarray(draws, np.int32)
+        used, rev = C.c_size_t(0), C.c_uint32(0)
+        self._check(self.L.lgca_b200_group_body_force(self.g, int(forcing), _ptr(draws), draws.size, C.byref(used), C.byref(rev)))
+        return int(used.value), int(rev.value)
+
+    def count_particles(self):
+        v = C.c_uint64(0)
+        self._check(self.L.lgca_b200_group_count_particles(self.g, C.byref(v)))
+        return int(v.value)
+
+    def init_random_device(self, seed=1):
+        self._check(self.L.lgca_b200_group_init_random_device(self.g, int(seed)))
+
+    def apply_bc_device(self, name):
+        self._check(self.L.lgca_b200_group_apply_bc_device(self.g, name.encode()))
+
+    def launch_count(self):
+        v = C.c_uint64(0)
+        self._check(self.L.lgca_b200_group_launch_count(self.g, C.byref(v)))
+        return int(v.value)
+
+    def info(self):
+        i = Info()
+        self._check(self.L.lgca_b200_group_get_info(self.g, C.byref(i)))
+        return i

@@ -82,10 +82,47 @@ int unalias_snapshot(lgca_b200_lattice* h)
     SnapLock lock(h);
     // the spare was the previous snapshot: the post stream may still be reading it
     LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_post, 0));
+    // strips: the copy takes the ghost rows along, so the neighbours' pushes of the current epoch must have landed
+    if (h->ring_connected && h->ring_epoch) {
+        int rc = ring_wait_current_epoch(h);
+        if (rc) return rc;
+    }
     LGCA_CUDA_CHECK(cudaMemcpyAsync(h->snap_spare, h->planes[h->cur], (size_t)h->g.plane_stride * sizeof(uint32_t) * h->nd,
                                     cudaMemcpyDeviceToDevice, h->s_compute));
     h->planes[h->cur] = h->snap_spare;
     h->snap_spare = nullptr;
+    return 0;
+}
+
+// Steps that ONE kernel launch can advance this handle (<= want).  A strip's ghost rows are refreshed only between
+// launches, so this is also the number of steps a strip may take per halo exchange: the fused depth the wavefront
+// kernel supports for this geometry, or 1 when only the generic kernel applies (dim_x < 64, fewer than 8 stored rows,
+// LGCA_B200_FLAG_SIMPLE_KERNEL).
+int steps_per_launch(const lgca_b200_lattice* h, int want)
+{
+    if (want < 1) return 1;
+    if (h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) return 1;
+    int k = std::min(h->k_fuse, want);
+    while (k > 1 && !wave_supported(h, k)) --k;
+    return std::max(k, 1);
+}
+} // namespace lgca_b200
+
+namespace lgca_b200 {
+// { sum of m_x/rho, sum of m_y/rho, number of FLUID cells } over the owned rows of the snapshot
+int mean_velocity_sums(lgca_b200_lattice* h, double out3[3])
+{
+    LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+    cudaStream_t s = h->s_post;
+    SnapLock lock(h);
+    LGCA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_snap, 0));
+    int rc = launch_mean_velocity(h, h->snap, h->d_scalars, s);
+    if (rc) return rc;
+    LGCA_CUDA_CHECK(cudaMemcpyAsync(h->h_scalars, h->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    LGCA_CUDA_CHECK(cudaEventRecord(h->ev_post, s));
+    lock.release();
+    LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
+    for (int i = 0; i < 3; ++i) out3[i] = h->h_scalars[i];
     return 0;
 }
 } // namespace lgca_b200
@@ -145,13 +182,20 @@ int lgca_b200_create(const lgca_b200_config* cfg, lgca_b200_lattice** out)
                             : ((cfg->model == LGCA_B200_HPP || (uint64_t)cfg->dim_x * (uint64_t)cfg->dim_y >= (1ull << 24)) ? 6 : 5);
     if (cfg->model != LGCA_B200_HPP && h->k_fuse > LGCA_MAX_K_FHP) h->k_fuse = LGCA_MAX_K_FHP;
 
+    h->sm_count = prop.multiProcessorCount;
     const bool whole = (cfg->y_rows == 0 || cfg->y_rows == cfg->dim_y);
     if (!whole) {
-        if (cfg->y_begin + cfg->y_rows > cfg->dim_y) { delete h; return set_error(LGCA_B200_EINVAL, "strip exceeds lattice"); }
-        if (cfg->cg_radius && (cfg->y_begin % (2 * cfg->cg_radius) || cfg->y_rows % (2 * cfg->cg_radius))) {
-            delete h;
-            return set_error(LGCA_B200_EINVAL, "strip bounds must be multiples of 2*cg_radius");
-        }
+        const uint32_t halo = (uint32_t)((std::max(h->k_fuse, 1) + 1) & ~1);
+        int bad = 0;
+        if ((uint64_t)cfg->y_begin + cfg->y_rows > cfg->dim_y) bad = set_error(LGCA_B200_EINVAL, "strip exceeds lattice");
+        else if (cfg->cg_radius && (cfg->y_begin % (2 * cfg->cg_radius) || cfg->y_rows % (2 * cfg->cg_radius)))
+            bad = set_error(LGCA_B200_EINVAL, "strip bounds must be multiples of 2*cg_radius");
+        else if (cfg->model != LGCA_B200_HPP && ((cfg->y_begin | cfg->y_rows) & 1u))
+            bad = set_error(LGCA_B200_EINVAL, "FHP strips must start on an even row and have an even height (hexagonal row parity)");
+        else if (cfg->y_rows < halo)
+            bad = set_error(LGCA_B200_EINVAL, "strip of %u rows is shorter than its halo of %u rows (k_fuse %d): lower k_fuse or use "
+                                              "fewer strips", cfg->y_rows, halo, h->k_fuse);
+        if (bad) { lgca_b200_destroy(h); return bad; }
     }
     Geom& g = h->g;
     g.dim_x  = cfg->dim_x;
@@ -176,6 +220,8 @@ int lgca_b200_create(const lgca_b200_config* cfg, lgca_b200_lattice** out)
     const size_t pw = plane_words(h) * sizeof(uint32_t);
     for (int i = 0; i < 2 && !rc; ++i) rc = dev_alloc(h, (void**)&h->planes[i], pw * h->nd, true);
     if (!rc) rc = dev_alloc(h, (void**)&h->snap, pw * h->nd, true);
+    h->base[0] = h->planes[0]; h->base[1] = h->planes[1]; h->base[2] = h->snap;
+    if (!rc && g.halo) rc = dev_alloc(h, (void**)&h->snap_ghost, (size_t)g.pitch * sizeof(uint32_t) * h->nd, true);
     if (!rc) rc = dev_alloc(h, (void**)&h->ns, pw, true);
     if (!rc) rc = dev_alloc(h, (void**)&h->sl, pw, true);
     if (!rc) rc = dev_alloc(h, (void**)&h->ch, pw, true);
@@ -209,9 +255,14 @@ int lgca_b200_destroy(lgca_b200_lattice* h)
     cudaDeviceSynchronize();
     lgca_b200_ring_disconnect(h);
     cudaFree(h->ring_flags);
-    if (h->snap_spare) { h->planes[h->cur] = h->snap_spare; h->snap_spare = nullptr; } // undo the alias: free each buffer once
-    for (int i = 0; i < 2; ++i) { cudaFree(h->planes[i]); cudaFree(h->d_stage[i]); }
-    cudaFree(h->snap); cudaFree(h->ns); cudaFree(h->sl); cudaFree(h->ch); cudaFree(h->xedge); cudaFree(h->d_flags);
+    if (h->base[0] || h->base[1] || h->base[2]) {
+        for (int i = 0; i < 3; ++i) cudaFree(h->base[i]); // the three plane sets, whatever their current roles
+    } else {
+        for (int i = 0; i < 2; ++i) cudaFree(h->planes[i]);
+        cudaFree(h->snap);
+    }
+    for (int i = 0; i < 2; ++i) cudaFree(h->d_stage[i]);
+    cudaFree(h->snap_ghost); cudaFree(h->ns); cudaFree(h->sl); cudaFree(h->ch); cudaFree(h->xedge); cudaFree(h->d_flags);
     cudaFree(h->d_cell_density); cudaFree(h->d_cell_momentum); cudaFree(h->d_mean_density); cudaFree(h->d_mean_momentum);
     cudaFree(h->d_scalars); cudaFree(h->d_draws); cudaFree(h->d_draw_bytes);
     if (h->h_scalars) cudaFreeHost(h->h_scalars);
@@ -288,6 +339,7 @@ int lgca_b200_upload(lgca_b200_lattice* h, const uint8_t* state, const int32_t* 
     }
     if (state) {
         if ((rc = unalias_snapshot(h))) return rc; // in-place write: the snapshot must not see it
+        if ((rc = ring_order_inplace_write(h))) return rc; // ... and my last ghost-row push has read the old edge rows
         // two-stage pipeline over the staging buffers: the copy engine (s_copy) moves chunk c+1 over PCIe while the
         // SMs (compute stream) transpose chunk c into bit-planes
         if ((rc = ensure_copy_stream(h))) return rc;
@@ -345,13 +397,13 @@ static int step_impl(lgca_b200_lattice* h, int n_steps, bool check_halo)
 {
     if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
     if (n_steps < 0) return set_error(LGCA_B200_EINVAL, "n_steps < 0");
-    // a strip's ghost rows are only refreshed by the halo exchange: one launch (<= k_fuse steps) per exchange
-    if (check_halo && h->g.halo && n_steps > h->k_fuse)
-        return set_error(LGCA_B200_ESTATE, "a strip can advance at most k_fuse=%d steps between halo exchanges", h->k_fuse);
+    // a strip's ghost rows are only refreshed by the halo exchange, and the step kernels write owned rows only:
+    // everything between two exchanges must fit ONE launch of the kernel that will actually run
+    if (check_halo && h->g.halo && n_steps > 1 && n_steps > steps_per_launch(h, n_steps))
+        return set_error(LGCA_B200_ESTATE, "this strip can advance at most %d step(s) between halo exchanges (k_fuse %d; the "
+                                           "generic kernel advances one step per exchange)", steps_per_launch(h, h->k_fuse), h->k_fuse);
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     const bool simple = (h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) != 0;
-    if (h->g.halo && simple && check_halo && n_steps > 1)
-        return set_error(LGCA_B200_ESTATE, "the generic kernel advances a strip one step per halo exchange");
     while (n_steps > 0) {
         int k = 1, rc;
         if (!simple) {
@@ -388,15 +440,19 @@ int lgca_b200_snapshot(lgca_b200_lattice* h)
         int rc = ring_wait_current_epoch(h);
         if (rc) return rc;
     }
-    if (h->g.halo == 0 && !h->ring_connected) {
-        // zero-copy: the live buffer becomes the snapshot (see lgca_internal.h); nothing to do if it already is
-        if (!h->snap_spare) {
-            h->snap_spare = h->snap;
-            h->snap = h->planes[h->cur];
-        }
-    } else {
-        LGCA_CUDA_CHECK(cudaMemcpyAsync(h->snap, h->planes[h->cur], plane_words(h) * sizeof(uint32_t) * h->nd,
-                                        cudaMemcpyDeviceToDevice, h->s_compute));
+    if (h->g.halo) {
+        // strips: the coarse means of the top coarse row read the first row beyond the owned rows; keep a side copy of
+        // it, so that the post stream never touches ghost rows (the neighbours keep storing into them)
+        const Geom& g = h->g;
+        LGCA_CUDA_CHECK(cudaMemcpy2DAsync(h->snap_ghost, (size_t)g.pitch * sizeof(uint32_t),
+                                          h->planes[h->cur] + (size_t)(g.rows - g.halo) * g.pitch,
+                                          (size_t)g.plane_stride * sizeof(uint32_t), (size_t)g.pitch * sizeof(uint32_t), h->nd,
+                                          cudaMemcpyDeviceToDevice, h->s_compute));
+    }
+    // zero-copy: the live buffer becomes the snapshot (see lgca_internal.h); nothing to do if it already is
+    if (!h->snap_spare) {
+        h->snap_spare = h->snap;
+        h->snap = h->planes[h->cur];
     }
     LGCA_CUDA_CHECK(cudaEventRecord(h->ev_snap, h->s_compute));
     return 0;
@@ -434,7 +490,7 @@ int lgca_b200_post_process(lgca_b200_lattice* h, float* cell_density, float* cel
             if ((rc = dev_alloc(h, (void**)&h->d_mean_density, std::max<size_t>(nc, 1) * sizeof(float), false))) return rc;
             if ((rc = dev_alloc(h, (void**)&h->d_mean_momentum, 2 * std::max<size_t>(nc, 1) * sizeof(float), false))) return rc;
         }
-        if ((rc = launch_mean_fields(h, h->snap, h->d_mean_density, h->d_mean_momentum, exact_order, s))) return rc;
+        if ((rc = launch_mean_fields(h, h->snap, h->g.halo ? h->snap_ghost : nullptr, h->d_mean_density, h->d_mean_momentum, exact_order, s))) return rc;
         if (mean_density)
             LGCA_CUDA_CHECK(cudaMemcpyAsync(mean_density, h->d_mean_density, nc * sizeof(float), cudaMemcpyDeviceToHost, s));
         if (mean_momentum)
@@ -449,19 +505,11 @@ int lgca_b200_post_process(lgca_b200_lattice* h, float* cell_density, float* cel
 int lgca_b200_mean_velocity(lgca_b200_lattice* h, float out[2])
 {
     if (!h || !out) return set_error(LGCA_B200_EINVAL, "null argument");
-    LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
-    cudaStream_t s = h->s_post;
-    SnapLock lock(h);
-    LGCA_CUDA_CHECK(cudaStreamWaitEvent(s, h->ev_snap, 0));
-    int rc = launch_mean_velocity(h, h->snap, h->d_scalars, s);
+    double s3[3];
+    int rc = mean_velocity_sums(h, s3);
     if (rc) return rc;
-    LGCA_CUDA_CHECK(cudaMemcpyAsync(h->h_scalars, h->d_scalars, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-    LGCA_CUDA_CHECK(cudaEventRecord(h->ev_post, s));
-    lock.release();
-    LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
-    const double n = h->h_scalars[2];
-    out[0] = (float)(h->h_scalars[0] / n);
-    out[1] = (float)(h->h_scalars[1] / n);
+    out[0] = (float)(s3[0] / s3[2]);
+    out[1] = (float)(s3[1] / s3[2]);
     return 0;
 }
 
@@ -531,6 +579,7 @@ int lgca_b200_body_force_apply(lgca_b200_lattice* h, const int32_t* cells, const
     memcpy(blob.data() + n * 4, new_bytes, n);
     LGCA_CUDA_CHECK(cudaMemcpyAsync(h->d_draws, blob.data(), blob.size(), cudaMemcpyHostToDevice, s));
     if ((rc = unalias_snapshot(h))) return rc; // in-place write: the snapshot must not see it
+    if ((rc = ring_order_inplace_write(h))) return rc;
     if ((rc = launch_apply_flips(h, h->planes[h->cur], h->d_draws, n, s))) return rc;
     LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
     return 0;
@@ -574,7 +623,9 @@ int lgca_b200_body_force_replay(int model, int bf_dir, int forcing, const int32_
                 touched[cell] = w;
             }
         }
-        if (!((int64_t)rev < (int64_t)forcing)) done = true; // do { ... } while (reverted < forcing && ...)
+        // do { ... } while (reverted_particles < forcing && ...): `unsigned int < int` compares as unsigned in the
+        // reference (src/omp_lattice.cpp:264,346), so a negative forcing never stops on the count
+        if (!(rev < (uint32_t)forcing)) done = true;
     }
     size_t k = 0;
     for (int32_t c : order) { changed_cells[k] = c; changed_bytes[k] = touched[c]; ++k; }
@@ -596,7 +647,7 @@ int lgca_b200_body_force(lgca_b200_lattice* h, int forcing, const int32_t* draws
     std::vector<int32_t> cells, ch_cells;
     std::vector<uint8_t> bytes, ch_bytes;
     size_t pos = 0;
-    int64_t remaining = forcing;
+    int64_t remaining = (int64_t)(uint32_t)forcing; // the reference's unsigned compare (negative forcing = "no limit")
     bool first = true;
     int rc;
     while (pos < n_draws && (first || remaining > 0)) {
@@ -608,7 +659,7 @@ int lgca_b200_body_force(lgca_b200_lattice* h, int forcing, const int32_t* draws
         size_t used = 0, nch = 0;
         uint32_t rev = 0;
         // a continuation batch must not re-run the reference's "at least one draw" rule
-        if ((rc = lgca_b200_body_force_replay(h->cfg.model, h->cfg.bf_dir, first ? (int)remaining : (int)std::max<int64_t>(remaining, 1),
+        if ((rc = lgca_b200_body_force_replay(h->cfg.model, h->cfg.bf_dir, (int)(uint32_t)(first ? remaining : std::max<int64_t>(remaining, 1)),
                                               cells.data(), bytes.data(), batch, &used, &rev, ch_cells.data(), ch_bytes.data(), &nch)))
             return rc;
         if ((rc = lgca_b200_body_force_apply(h, ch_cells.data(), ch_bytes.data(), nch))) return rc;
@@ -626,6 +677,7 @@ int lgca_b200_init_random_device(lgca_b200_lattice* h, uint64_t seed)
     if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     int rc = unalias_snapshot(h);
+    if (!rc) rc = ring_order_inplace_write(h);
     if (!rc) rc = launch_init_random(h, h->planes[h->cur], seed, h->s_compute);
     if (rc) return rc;
     LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
@@ -684,8 +736,7 @@ int lgca_b200_timed_kernel(lgca_b200_lattice* h, int launches, float* ms_per_lau
 {
     if (!h || !ms_per_launch || launches <= 0) return set_error(LGCA_B200_EINVAL, "bad argument");
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
-    int k = h->k_fuse;
-    while (k > 1 && !wave_supported(h, k)) --k;
+    const int k = steps_per_launch(h, h->k_fuse);
     LGCA_CUDA_CHECK(cudaEventRecord(h->ev_t0, h->s_compute));
     int rc = step_impl(h, k * launches, false);
     if (rc) return rc;
@@ -723,6 +774,13 @@ int lgca_b200_halo_rows(lgca_b200_lattice* h, uint32_t* rows)
 {
     if (!h || !rows) return set_error(LGCA_B200_EINVAL, "null argument");
     *rows = h->g.halo;
+    return 0;
+}
+
+int lgca_b200_steps_per_exchange(lgca_b200_lattice* h, int* steps)
+{
+    if (!h || !steps) return set_error(LGCA_B200_EINVAL, "null argument");
+    *steps = h->g.halo ? std::min(steps_per_launch(h, h->k_fuse), (int)h->g.halo) : h->k_fuse;
     return 0;
 }
 

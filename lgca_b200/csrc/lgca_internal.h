@@ -36,6 +36,14 @@ struct lgca_b200_lattice {
     // in place first calls unalias_snapshot() (copy-on-write).  Strips keep the copy: the ring neighbours hold fixed
     // mappings of planes[0] / planes[1].
     uint32_t*        snap_spare;
+    // The three plane sets behind planes[0] / planes[1] / snap in allocation order.  They rotate (zero-copy snapshot),
+    // so ring neighbours address a peer's buffer by its index in this array: all strips of a lattice perform the same
+    // sequence of steps / snapshots / in-place writes, hence the live buffer has the same index on every strip.
+    uint32_t*        base[3];
+    // strips: the one row beyond the owned rows that the coarse means of the top coarse row read (first row of the
+    // upper neighbour), copied at snapshot time so that post-processing never reads ghost rows of a rotating buffer
+    uint32_t*        snap_ghost;  // [nd][pitch]
+    int              sm_count;    // multiProcessorCount of the handle's device
     uint32_t*        ns;          // no-slip solid mask plane  [rows][pitch]
     uint32_t*        sl;          // slip solid mask plane
     uint32_t*        ch;          // chirality plane
@@ -73,9 +81,11 @@ struct lgca_b200_lattice {
     uint64_t         launches;
     uint64_t         device_bytes;
     // native halo ring (lgca_ring.cu)
-    void*            ring_flags;            // [2] epochs published by my lower / upper neighbour
-    void*            ring_lower_planes[2];  // the lower neighbour's ping-pong plane sets (peer / IPC mapping)
-    void*            ring_upper_planes[2];
+    void*            ring_flags;            // [0..1] epochs published by my lower / upper neighbour, [2..3] their acks
+    void*            ring_lower_planes[3];  // the lower neighbour's three plane sets (peer / IPC mapping), by base[] index
+    void*            ring_upper_planes[3];
+    uint32_t         ring_lower_rows;       // stored rows / plane stride of the neighbours (strips may differ in height)
+    uint64_t         ring_lower_stride, ring_upper_stride;
     void*            ring_lower_flags;
     void*            ring_upper_flags;
     int              ring_lower_ipc, ring_upper_ipc, ring_connected;
@@ -105,8 +115,15 @@ bool wave_supported(const lgca_b200_lattice* h, int k);
 int wave_prepare(lgca_b200_lattice* h);
 bool wave_has_edge_chunks(lgca_b200_lattice* h, int k);
 int simple_prepare(lgca_b200_lattice* h);
-int ring_wait_current_epoch(lgca_b200_lattice* h);
-int unalias_snapshot(lgca_b200_lattice* h); // lgca_capi.cu: give the live state a buffer of its own before an in-place write // lgca_ring.cu: stream-ordered wait for the neighbours' latest pushes
+int ring_wait_current_epoch(lgca_b200_lattice* h); // lgca_ring.cu: stream-ordered wait for the neighbours' latest pushes
+int ring_order_inplace_write(lgca_b200_lattice* h); // lgca_ring.cu: the compute stream waits for my last ghost-row push
+int unalias_snapshot(lgca_b200_lattice* h); // lgca_capi.cu: give the live state a buffer of its own before an in-place write
+int mean_velocity_sums(lgca_b200_lattice* h, double out3[3]); // lgca_capi.cu
+int steps_per_launch(const lgca_b200_lattice* h, int want); // lgca_capi.cu: steps ONE kernel launch can advance (<= want)
+inline int buffer_id(const lgca_b200_lattice* h, const uint32_t* p)
+{
+    return p == h->base[0] ? 0 : (p == h->base[1] ? 1 : (p == h->base[2] ? 2 : -1));
+}
 
 // lgca_pack.cu : reference layouts <-> bit-planes
 int launch_pack_state(lgca_b200_lattice* h, const uint8_t* d_bytes, uint32_t* planes, uint32_t row0, uint32_t nrows,
@@ -120,8 +137,8 @@ int launch_build_xedge(lgca_b200_lattice* h, cudaStream_t s);
 
 // lgca_post.cu : popcount reductions and field kernels
 int launch_cell_fields(lgca_b200_lattice* h, const uint32_t* planes, float* d_rho, float* d_mom, cudaStream_t s);
-int launch_mean_fields(lgca_b200_lattice* h, const uint32_t* planes, float* d_mrho, float* d_mmom, int exact,
-                       cudaStream_t s);
+int launch_mean_fields(lgca_b200_lattice* h, const uint32_t* planes, const uint32_t* ghost_row, float* d_mrho, float* d_mmom,
+                       int exact, cudaStream_t s);
 int launch_mean_velocity(lgca_b200_lattice* h, const uint32_t* planes, double* d_out3, cudaStream_t s);
 int launch_count_particles(lgca_b200_lattice* h, const uint32_t* planes, unsigned long long* d_out, cudaStream_t s);
 int launch_gather_cells(lgca_b200_lattice* h, const uint32_t* planes, const int32_t* d_cells, size_t n, uint8_t* d_bytes,

@@ -58,7 +58,8 @@ __global__ void __launch_bounds__(256) cell_fields_kernel(const uint32_t* __rest
 // exact integers / half-integers (popcounts); momentum-y is s * integer in the popcount path or the
 // reference's sequential row-major float32 sum when EXACT.
 template <int ND, bool EXACT>
-__global__ void __launch_bounds__(128) mean_fields_kernel(const uint32_t* __restrict__ planes, float* __restrict__ mrho,
+__global__ void __launch_bounds__(128) mean_fields_kernel(const uint32_t* __restrict__ planes,
+                                                          const uint32_t* __restrict__ ghost_row, float* __restrict__ mrho,
                                                           float* __restrict__ mmom, const Geom g, uint32_t cg,
                                                           uint32_t coarse_dim_x, uint32_t coarse_rows,
                                                           uint32_t coarse_row0)
@@ -79,7 +80,11 @@ __global__ void __launch_bounds__(128) mean_fields_kernel(const uint32_t* __rest
         if (gy >= g.dim_y) break;                 // neighbor_idx >= num_cells
         const uint32_t sy = gy - g.y0 + g.halo;   // stored row (strip rows + upper halo)
         ++nrows;
-        const size_t rb = (size_t)sy * g.pitch;
+        // strips: the row just above the owned rows comes from the side copy taken at snapshot time ([plane][pitch])
+        const bool   beyond = ghost_row != nullptr && sy >= g.rows - g.halo;
+        const uint32_t* src = beyond ? ghost_row : planes;
+        const size_t pstride = beyond ? (size_t)g.pitch : (size_t)g.plane_stride;
+        const size_t rb = beyond ? 0 : (size_t)sy * g.pitch;
         for (uint32_t w = ax >> 5; w <= (x1 >> 5); ++w) {
             uint32_t m = 0xFFFFFFFFu;
             if (w == (ax >> 5)) m &= 0xFFFFFFFFu << (ax & 31);
@@ -87,7 +92,7 @@ __global__ void __launch_bounds__(128) mean_fields_kernel(const uint32_t* __rest
             uint32_t v[7];
 #pragma unroll
             for (int d = 0; d < ND; ++d) {
-                v[d] = __ldg(planes + (size_t)d * g.plane_stride + rb + w) & m;
+                v[d] = __ldg(src + (size_t)d * pstride + rb + w) & m;
                 pc[d] += __popc(v[d]);
             }
             if (EXACT && ND != 4) {
@@ -247,8 +252,8 @@ int launch_cell_fields(lgca_b200_lattice* h, const uint32_t* planes, float* d_rh
     return 0;
 }
 
-int launch_mean_fields(lgca_b200_lattice* h, const uint32_t* planes, float* d_mrho, float* d_mmom, int exact,
-                       cudaStream_t s)
+int launch_mean_fields(lgca_b200_lattice* h, const uint32_t* planes, const uint32_t* ghost_row, float* d_mrho, float* d_mmom,
+                       int exact, cudaStream_t s)
 {
     const Geom& g = h->g;
     const uint32_t cg = h->cfg.cg_radius;
@@ -257,7 +262,7 @@ int launch_mean_fields(lgca_b200_lattice* h, const uint32_t* planes, float* d_mr
     const uint32_t cdx = g.dim_x / (2 * cg), crows = own / (2 * cg), crow0 = g.y0 / (2 * cg);
     if (cdx == 0 || crows == 0) return 0;
     dim3 grid((cdx + 127) / 128, crows, 1);
-#define MF(ND, EX) mean_fields_kernel<ND, EX><<<grid, 128, 0, s>>>(planes, d_mrho, d_mmom, g, cg, cdx, crows, crow0)
+#define MF(ND, EX) mean_fields_kernel<ND, EX><<<grid, 128, 0, s>>>(planes, ghost_row, d_mrho, d_mmom, g, cg, cdx, crows, crow0)
     if (exact) DISPATCH_ND(h->nd, (MF(4, true)), (MF(6, true)), (MF(7, true)));
     else       DISPATCH_ND(h->nd, (MF(4, false)), (MF(6, false)), (MF(7, false)));
 #undef MF
@@ -285,7 +290,7 @@ int launch_count_particles(lgca_b200_lattice* h, const uint32_t* planes, unsigne
     const Geom& g = h->g;
     const uint32_t own = g.rows - 2 * g.halo;
     LGCA_CUDA_CHECK(cudaMemsetAsync(d_out, 0, sizeof(unsigned long long), s));
-    count_kernel<<<148 * 8, 256, 0, s>>>(planes, d_out, g, h->nd, own);
+    count_kernel<<<(h->sm_count > 0 ? h->sm_count : 148) * 8, 256, 0, s>>>(planes, d_out, g, h->nd, own);
     h->launches++;
     LGCA_CUDA_CHECK(cudaGetLastError());
     return 0;

@@ -13,9 +13,21 @@
 // Safety: a neighbour only starts reading its B ghost rows after my signal b+1; and I only overwrite its A ghost
 // rows at the end of block b+1, which I started after its signal b+1, i.e. after its block-b kernel (the last
 // reader of A) had finished.  The step kernel never stores ghost rows, so pushes cannot be clobbered.
-#include <stdlib.h>
+//
+// Three plane sets rotate per strip (zero-copy snapshot, lgca_internal.h).  Every strip of a lattice issues the same
+// sequence of steps / snapshots / in-place writes, so the live set has the same index on every strip and a push
+// addresses the neighbour's set by that index.  With three sets the buffer a push overwrites was last read by a step
+// kernel even earlier than in the two-buffer argument above; post-processing never reads ghost rows of the big
+// buffers (the snapshot keeps a side copy of the one row it needs).
+//
+// Publishing WITHOUT a step in between (lgca_b200_ring_start / lgca_b200_ring_republish: after an upload, an
+// initialiser or a body force changed the edge rows): the ghost rows being replaced may still be read by the
+// neighbour's stream (its last step kernel, a snapshot side copy), so the publish first handshakes -- every strip
+// posts an ACK ("my compute stream has passed every reader of epoch e") to both neighbours and waits for theirs.
 #include <string.h>
 #include <unistd.h>
+
+#include <algorithm>
 
 #include "lgca_internal.h"
 
@@ -26,16 +38,17 @@ struct RingBlob { // what a rank publishes to its neighbours
     int32_t            pid, device;
     uint32_t           rows, pitch, halo, nd;
     uint64_t           plane_stride;
-    void*              raw_planes[2]; // valid inside the publishing process
+    void*              raw_planes[3]; // valid inside the publishing process
     void*              raw_flags;
-    cudaIpcMemHandle_t ipc_planes[2];
+    cudaIpcMemHandle_t ipc_planes[3];
     cudaIpcMemHandle_t ipc_flags;
 };
 static const uint64_t RING_MAGIC = 0x4C47434152494E47ull; // "LGCARING"
 
 // copies `halo` rows of every plane: src rows [src_row, src_row+halo) -> dst rows [dst_row, ...)
 __global__ void __launch_bounds__(256) ring_push_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst_upper,
-                                                        uint32_t* __restrict__ dst_lower, Geom g, int nd)
+                                                        uint32_t* __restrict__ dst_lower, Geom g, int nd,
+                                                        uint64_t upper_stride, uint64_t lower_stride, uint32_t lower_rows)
 {
     // x = word in [0, halo*pitch) as uint4, y = plane, z = 0: top rows -> upper neighbour, 1: bottom rows -> lower
     const uint32_t n4 = g.halo * g.pitch / 4;
@@ -46,11 +59,11 @@ __global__ void __launch_bounds__(256) ring_push_kernel(const uint32_t* __restri
     if (blockIdx.z == 0) {
         // my highest owned rows become the upper neighbour's lower ghost rows [0, halo)
         const uint4 v = reinterpret_cast<const uint4*>(src + plane + (size_t)(g.rows - 2 * g.halo) * g.pitch)[i];
-        reinterpret_cast<uint4*>(dst_upper + plane)[i] = v;
+        reinterpret_cast<uint4*>(dst_upper + (size_t)d * upper_stride)[i] = v;
     } else {
         // my lowest owned rows become the lower neighbour's upper ghost rows [rows-halo, rows)
         const uint4 v = reinterpret_cast<const uint4*>(src + plane + (size_t)g.halo * g.pitch)[i];
-        reinterpret_cast<uint4*>(dst_lower + plane + (size_t)(g.rows - g.halo) * g.pitch)[i] = v;
+        reinterpret_cast<uint4*>(dst_lower + (size_t)d * lower_stride + (size_t)(lower_rows - g.halo) * g.pitch)[i] = v;
     }
 }
 
@@ -66,7 +79,7 @@ __global__ void ring_signal_kernel(volatile uint32_t* upper_flag_from_lower, vol
 
 __global__ void ring_wait_kernel(volatile uint32_t* my_flags, uint32_t epoch)
 {
-    // my_flags[0]: published by my lower neighbour, my_flags[1]: by my upper neighbour
+    // my_flags[0]: published by my lower neighbour, my_flags[1]: by my upper neighbour ([2], [3]: their acks)
     while (my_flags[threadIdx.x] < epoch) __nanosleep(200);
     __threadfence_system();
 }
@@ -75,10 +88,11 @@ __global__ void ring_wait_kernel(volatile uint32_t* my_flags, uint32_t epoch)
 static int ring_push_and_signal(lgca_b200_lattice* h, cudaStream_t s)
 {
     const Geom& g = h->g;
-    const int b = h->cur;
+    const int b = buffer_id(h, h->planes[h->cur]); // same index on every strip (lockstep rotation)
+    if (b < 0) return set_error(LGCA_B200_ESTATE, "live plane set is not one of the handle's three buffers");
     dim3 grid((g.halo * g.pitch / 4 + 255) / 256, h->nd, 2);
-    ring_push_kernel<<<grid, 256, 0, s>>>(h->planes[b], (uint32_t*)h->ring_upper_planes[b], (uint32_t*)h->ring_lower_planes[b],
-                                          g, h->nd);
+    ring_push_kernel<<<grid, 256, 0, s>>>(h->planes[h->cur], (uint32_t*)h->ring_upper_planes[b], (uint32_t*)h->ring_lower_planes[b],
+                                          g, h->nd, h->ring_upper_stride, h->ring_lower_stride, h->ring_lower_rows);
     h->launches++;
     LGCA_CUDA_CHECK(cudaGetLastError());
     h->ring_epoch++;
@@ -97,7 +111,15 @@ int ring_wait_current_epoch(lgca_b200_lattice* h)
     return 0;
 }
 
-static int open_peer(const RingBlob& blob, int my_device, void* planes[2], void** flags)
+// the compute stream waits for my most recent ghost-row push (it reads the edge rows an in-place writer is about to change)
+int ring_order_inplace_write(lgca_b200_lattice* h)
+{
+    if (!h->ring_connected || h->ring_blocks == 0) return 0;
+    LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_push[(h->ring_blocks - 1) & 1u], 0));
+    return 0;
+}
+
+static int open_peer(const RingBlob& blob, int my_device, void* planes[3], void** flags)
 {
     if (blob.magic != RING_MAGIC) return set_error(LGCA_B200_EINVAL, "not a ring descriptor");
     if (blob.pid == (int32_t)getpid()) {
@@ -110,13 +132,11 @@ static int open_peer(const RingBlob& blob, int my_device, void* planes[2], void*
             if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return set_cuda_error(e, "cudaDeviceEnablePeerAccess", __FILE__, __LINE__);
             cudaGetLastError();
         }
-        planes[0] = blob.raw_planes[0];
-        planes[1] = blob.raw_planes[1];
+        for (int i = 0; i < 3; ++i) planes[i] = blob.raw_planes[i];
         *flags = blob.raw_flags;
         return 0;
     }
-    LGCA_CUDA_CHECK(cudaIpcOpenMemHandle(&planes[0], blob.ipc_planes[0], cudaIpcMemLazyEnablePeerAccess));
-    LGCA_CUDA_CHECK(cudaIpcOpenMemHandle(&planes[1], blob.ipc_planes[1], cudaIpcMemLazyEnablePeerAccess));
+    for (int i = 0; i < 3; ++i) LGCA_CUDA_CHECK(cudaIpcOpenMemHandle(&planes[i], blob.ipc_planes[i], cudaIpcMemLazyEnablePeerAccess));
     LGCA_CUDA_CHECK(cudaIpcOpenMemHandle(flags, blob.ipc_flags, cudaIpcMemLazyEnablePeerAccess));
     return 1; // opened through IPC: must be closed
 }
@@ -160,11 +180,11 @@ int lgca_b200_ring_export(lgca_b200_lattice* h, void* descriptor, size_t bytes)
     b.device = h->cfg.device;
     b.rows = h->g.rows; b.pitch = h->g.pitch; b.halo = h->g.halo; b.nd = (uint32_t)h->nd;
     b.plane_stride = h->g.plane_stride;
-    b.raw_planes[0] = h->planes[0];
-    b.raw_planes[1] = h->planes[1];
+    for (int i = 0; i < 3; ++i) {
+        b.raw_planes[i] = h->base[i];
+        LGCA_CUDA_CHECK(cudaIpcGetMemHandle(&b.ipc_planes[i], h->base[i]));
+    }
     b.raw_flags = h->ring_flags;
-    LGCA_CUDA_CHECK(cudaIpcGetMemHandle(&b.ipc_planes[0], h->planes[0]));
-    LGCA_CUDA_CHECK(cudaIpcGetMemHandle(&b.ipc_planes[1], h->planes[1]));
     LGCA_CUDA_CHECK(cudaIpcGetMemHandle(&b.ipc_flags, h->ring_flags));
     memcpy(descriptor, &b, sizeof(b));
     return 0;
@@ -183,16 +203,17 @@ int lgca_b200_ring_connect(lgca_b200_lattice* h, const void* lower_descriptor, c
         if (b->pitch != h->g.pitch || b->halo != h->g.halo || b->nd != (uint32_t)h->nd)
             return set_error(LGCA_B200_EINVAL, "neighbour strip has a different geometry (pitch/halo/planes)");
     }
-    // ghost-row destinations are addressed with MY row count / plane stride: strips must have equal heights
-    if (lo.plane_stride != h->g.plane_stride || up.plane_stride != h->g.plane_stride)
-        return set_error(LGCA_B200_EINVAL, "native ring needs strips of equal height (plane stride differs)");
+    // ghost-row destinations are addressed with the NEIGHBOUR's row count / plane stride (strips may differ in height)
+    h->ring_lower_rows = lo.rows;
+    h->ring_lower_stride = lo.plane_stride;
+    h->ring_upper_stride = up.plane_stride;
+    // every strip must rotate its buffers in lockstep: start from the same live index
     int rc = open_peer(lo, h->cfg.device, h->ring_lower_planes, &h->ring_lower_flags);
     if (rc < 0) return rc;
     h->ring_lower_ipc = rc;
     const bool same = memcmp(&lo, &up, sizeof(lo)) == 0; // world == 2: both neighbours are the same strip
     if (same) {
-        h->ring_upper_planes[0] = h->ring_lower_planes[0];
-        h->ring_upper_planes[1] = h->ring_lower_planes[1];
+        for (int i = 0; i < 3; ++i) h->ring_upper_planes[i] = h->ring_lower_planes[i];
         h->ring_upper_flags = h->ring_lower_flags;
         h->ring_upper_ipc = 0;
     } else {
@@ -213,21 +234,34 @@ int lgca_b200_ring_connect(lgca_b200_lattice* h, const void* lower_descriptor, c
     return 0;
 }
 
-// Publishes the current edge rows to the neighbours (epoch 1).  Call on every rank after upload / init and
-// after connect, before the first lgca_b200_ring_step.
-int lgca_b200_ring_start(lgca_b200_lattice* h)
+// Publishes the current edge rows to the neighbours without a step in between: after upload / init (first call:
+// epoch 1) and after anything that changed the live state in place (body force, a new upload).  Collective: every
+// strip of the lattice must call it at the same point of its call sequence.  Stream-ordered, no host synchronisation:
+//     wait for my last push -> ACK to both neighbours -> wait for their ACKs -> push -> signal (next epoch)
+int lgca_b200_ring_republish(lgca_b200_lattice* h)
 {
     if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
     if (!h->ring_connected) return set_error(LGCA_B200_ESTATE, "ring not connected");
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
-    // everything queued so far (upload, init, earlier ring traffic) precedes the first push
-    LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_ring));
-    int rc = ring_push_and_signal(h, h->s_compute);
+    int rc = ring_order_inplace_write(h);
     if (rc) return rc;
-    LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
-    h->ring_blocks = 0;
+    const uint32_t next = h->ring_epoch + 1;
+    // my compute stream has passed every reader of my ghost rows (step kernels, snapshot side copies): tell the
+    // neighbours they may overwrite them; slot 2 = ack from the lower neighbour, slot 3 = from the upper one
+    ring_signal_kernel<<<1, 1, 0, h->s_compute>>>((volatile uint32_t*)h->ring_upper_flags + 2, (volatile uint32_t*)h->ring_lower_flags + 3, next);
+    h->launches++;
+    LGCA_CUDA_CHECK(cudaGetLastError());
+    ring_wait_kernel<<<1, 2, 0, h->s_compute>>>((volatile uint32_t*)h->ring_flags + 2, next);
+    h->launches++;
+    LGCA_CUDA_CHECK(cudaGetLastError());
+    if ((rc = ring_push_and_signal(h, h->s_compute))) return rc;
+    LGCA_CUDA_CHECK(cudaEventRecord(h->ev_push[h->ring_blocks & 1u], h->s_compute));
+    h->ring_blocks++;
     return 0;
 }
+
+// First publish after upload / init and connect, before the first lgca_b200_ring_step (kept as its own entry point).
+int lgca_b200_ring_start(lgca_b200_lattice* h) { return lgca_b200_ring_republish(h); }
 
 int lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps)
 {
@@ -236,20 +270,17 @@ int lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps)
     if (h->ring_epoch == 0) return set_error(LGCA_B200_ESTATE, "call lgca_b200_ring_start first");
     if (n_steps < 0) return set_error(LGCA_B200_EINVAL, "n_steps < 0");
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
-    const bool simple = (h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) != 0;
-    const int block = simple ? 1 : h->k_fuse;
-    // timing experiments only (results are wrong with these): 1 = no ghost-row wait, 2 = no push/signal, 3 = neither
-    static int dbg = -1;
-    if (dbg < 0) { const char* e = getenv("LGCA_B200_RING_DEBUG"); dbg = e ? atoi(e) : 0; }
+    // one kernel launch per exchange: the fused depth of the wavefront kernel, or 1 for the generic kernel
+    const int block = std::min(steps_per_launch(h, h->k_fuse), (int)h->g.halo);
     while (n_steps > 0) {
         const int k = n_steps < block ? n_steps : block;
         const int slot = (int)(h->ring_blocks & 1u);
-        // (WAR) this block overwrites the edge rows that the push two blocks ago read
+        // (WAR) this block overwrites edge rows that an earlier push read (pushes complete in order on s_ring)
         if (h->ring_blocks >= 2) LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_push[slot], 0));
         int rc;
-        if (!simple && wave_has_edge_chunks(h, k)) {
+        if (!(h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) && wave_has_edge_chunks(h, k)) {
             // tiles that read ghost rows wait in-kernel; the rest of the strip starts immediately
-            h->ring_inkernel_epoch = (dbg & 1) ? 0 : h->ring_epoch;
+            h->ring_inkernel_epoch = h->ring_epoch;
             rc = lgca_b200_step(h, k);
             h->ring_inkernel_epoch = 0;
         } else {
@@ -262,8 +293,7 @@ int lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps)
         // push + signal overlap with the next block's interior tiles
         LGCA_CUDA_CHECK(cudaEventRecord(h->ev_step[slot], h->s_compute));
         LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_ring, h->ev_step[slot], 0));
-        if (dbg & 2) h->ring_epoch++;
-        else if ((rc = ring_push_and_signal(h, h->s_ring))) return rc;
+        if ((rc = ring_push_and_signal(h, h->s_ring))) return rc;
         LGCA_CUDA_CHECK(cudaEventRecord(h->ev_push[slot], h->s_ring));
         h->ring_blocks++;
         n_steps -= k;
@@ -279,13 +309,11 @@ int lgca_b200_ring_disconnect(lgca_b200_lattice* h)
     cudaStreamSynchronize(h->s_compute);
     if (h->s_ring) cudaStreamSynchronize(h->s_ring);
     if (h->ring_lower_ipc) {
-        cudaIpcCloseMemHandle(h->ring_lower_planes[0]);
-        cudaIpcCloseMemHandle(h->ring_lower_planes[1]);
+        for (int i = 0; i < 3; ++i) cudaIpcCloseMemHandle(h->ring_lower_planes[i]);
         cudaIpcCloseMemHandle(h->ring_lower_flags);
     }
     if (h->ring_upper_ipc) {
-        cudaIpcCloseMemHandle(h->ring_upper_planes[0]);
-        cudaIpcCloseMemHandle(h->ring_upper_planes[1]);
+        for (int i = 0; i < 3; ++i) cudaIpcCloseMemHandle(h->ring_upper_planes[i]);
         cudaIpcCloseMemHandle(h->ring_upper_flags);
     }
     cudaGetLastError();

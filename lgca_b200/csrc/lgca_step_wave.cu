@@ -88,8 +88,17 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
     return v;
 }
 
+// Plane loads.  Default: the read-only path (ld.global.nc) -- neighbouring bands share two words per row through L1.
+// COH (the two EDGE chunks of a strip while the native ring is running): ghost rows are stored by the neighbour GPU
+// during the kernel's lifetime, which the .nc path is not defined for (a narrow row shares its 128-byte line with rows
+// an interior tile may have pulled into L1 before the push arrived), so those tiles load through L2 (ld.global.cg)
+// after their acquire of the epoch flag.  Interior tiles never touch a ghost row (the prefetch is clamped to the
+// tile's input rows) and keep the faster path.
+template <bool COH>
+__device__ __forceinline__ uint32_t ld_plane(const uint32_t* p) { return COH ? __ldcg(p) : __ldg(p); }
+
 // Per-lane view of the periodic row: where this lane's 32 sites come from.
-template <bool IRREG>
+template <bool IRREG, bool COH = false>
 struct LaneSrc {
     uint32_t wa, wb;
     int      sh, n1;
@@ -97,14 +106,11 @@ struct LaneSrc {
     // row_off = word offset of the row start inside a plane
     __device__ __forceinline__ uint32_t load(const uint32_t* __restrict__ plane, uint32_t row_off) const
     {
-        // Read-only path (ld.global.nc): neighbouring bands share two words per row through L1.  Safe next to the
-        // ring's in-kernel arrival of ghost rows because no tile ever touches a ghost row it does not need
-        // (the prefetch is clamped to the tile's input rows) and tiles that need them wait for the flag first.
-        uint32_t v = __ldg(plane + (row_off + wa));
+        uint32_t v = ld_plane<COH>(plane + (row_off + wa));
         if (IRREG) {
             if (!regular) { // lanes at the row end of a width that is not a multiple of 32
-                v = __funnelshift_r(v, __ldg(plane + (row_off + wb)), sh);
-                if (n1 < 32) v = (v & low_mask(n1)) | (__ldg(plane + row_off) << n1);
+                v = __funnelshift_r(v, ld_plane<COH>(plane + (row_off + wb)), sh);
+                if (n1 < 32) v = (v & low_mask(n1)) | (ld_plane<COH>(plane + row_off) << n1);
             }
         }
         return v;
@@ -120,7 +126,7 @@ struct LaneSrc {
         if (!IRREG) {
             const char* pr = (const char*)(planes[0] + (row_off + wa));
 #pragma unroll
-            for (int d = 0; d < ND; ++d) v[d] = __ldg((const uint32_t*)(pr + (uint64_t)stride_bytes * (uint32_t)d));
+            for (int d = 0; d < ND; ++d) v[d] = ld_plane<COH>((const uint32_t*)(pr + (uint64_t)stride_bytes * (uint32_t)d));
         } else {
 #pragma unroll
             for (int d = 0; d < ND; ++d) v[d] = load(planes[d], row_off);
@@ -145,8 +151,8 @@ struct WaveState {
 // One iteration: level-0 row r0 arrives, every level s produces its row r0 - s, and the level-K row
 // r0 - K is stored.  PAR = parity of the iteration index (compile time); WARM = pipeline still filling
 // (levels whose inputs are not there yet are skipped, nothing is stored before iteration 2K).
-template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG, int PAR, bool WARM>
-__device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG>& src, int jc, int fetch_end,
+template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG, bool COH, int PAR, bool WARM>
+__device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG, COH>& src, int jc, int fetch_end,
                                          uint32_t plane_words, uint32_t out_off, const WaveArgs& A, const Geom& g,
                                          uint32_t ew, bool store_lane, uint32_t vmask)
 {
@@ -301,10 +307,10 @@ __device__ __forceinline__ void tile_rows(const Geom& g, const WavePlan& wp, int
 //   * width a multiple of 32: every lane reads one plain word at a wrapped index;
 //   * otherwise lanes whose 32 sites touch the row end assemble them from up to three words
 //     (two around bit position p, plus word 0 after the wrap) with precomputed indices/shifts.
-template <bool IRREG>
-__device__ __forceinline__ LaneSrc<IRREG> make_lane_src(const Geom& g, int wi)
+template <bool IRREG, bool COH = false>
+__device__ __forceinline__ LaneSrc<IRREG, COH> make_lane_src(const Geom& g, int wi)
 {
-    LaneSrc<IRREG> src;
+    LaneSrc<IRREG, COH> src;
     src.wb = 0; src.sh = 0; src.n1 = 32; src.regular = true;
     int wa = wi;
     if (!IRREG) {
@@ -326,14 +332,14 @@ __device__ __forceinline__ LaneSrc<IRREG> make_lane_src(const Geom& g, int wi)
 }
 
 // One tile (band x chunk) of the fused-step kernel.
-template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
+template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG, bool COH>
 __device__ __forceinline__ void wave_tile(const WaveArgs& A, const Geom& g, const WavePlan& wp, const int band, const int c)
 {
     constexpr int ND = num_dir_of(MODEL);
     const int lane = threadIdx.x;
     int oa, ob;
     tile_rows(g, wp, c, oa, ob);
-    if (wp.edge_rows && A.ring_flags && c < 2) {
+    if (COH) {
         // in-kernel halo wait: only the edge tiles depend on the neighbours' pushes; everyone else starts at once
         if (lane == 0) {
             if (c == 0) while (ld_acquire_sys(A.ring_flags + 0) < A.ring_epoch) __nanosleep(64);
@@ -349,7 +355,7 @@ __device__ __forceinline__ void wave_tile(const WaveArgs& A, const Geom& g, cons
     const int total = (yb - ya) + 2 * K;                     // level-0 rows to push through
     const int rows  = (int)g.rows;
 
-    const LaneSrc<IRREG> src = make_lane_src<IRREG>(g, wi);
+    const LaneSrc<IRREG, COH> src = make_lane_src<IRREG, COH>(g, wi);
     const bool     store_lane = (lane >= 1) && (lane <= WAVE_VALID) && (wi < (int)g.nw);
     const uint32_t vmask      = store_lane ? valid_mask(g, wi) : 0u;
     const uint32_t ew         = HAS_SL ? src.load(A.xedge, 0u) : 0u;
@@ -383,7 +389,7 @@ __device__ __forceinline__ void wave_tile(const WaveArgs& A, const Geom& g, cons
     // word offset of the row stored by the current iteration (row ya - 2K + jc), advanced per row
     uint32_t out_off = (uint32_t)ya * g.pitch + (uint32_t)max(wi, 0);
 #define LGCA_ROW(PAR, WARM, JC)                                                                                      \
-    wave_row<MODEL, K, HAS_NS, HAS_SL, IRREG, PAR, WARM>(st, src, JC, fetch_end, plane_words, out_off, A, g, ew, store_lane, vmask)
+    wave_row<MODEL, K, HAS_NS, HAS_SL, IRREG, COH, PAR, WARM>(st, src, JC, fetch_end, plane_words, out_off, A, g, ew, store_lane, vmask)
     // pipeline fill: iterations 0 .. 2K-1 store nothing (2K is even, so parities alternate from 0)
 #pragma unroll 1
     for (int j = 0; j < 2 * K; j += 2) {
@@ -417,14 +423,17 @@ __global__ void __launch_bounds__(32, wave_min_blocks<MODEL, K, HAS_NS, HAS_SL, 
 {
     const int band = blockIdx.x;
     const int c    = blockIdx.y;
-    if ((HAS_NS || HAS_SL) && A.tile_fluid != nullptr && A.tile_fluid[c * wp.bands + band] != 0)
-        wave_tile<MODEL, K, false, false, IRREG>(A, g, wp, band, c);
+    if (wp.edge_rows && A.ring_flags && c < 2) // edge chunk of a strip on the native ring: flag wait + coherent loads
+        wave_tile<MODEL, K, HAS_NS, HAS_SL, IRREG, true>(A, g, wp, band, c);
+    else if ((HAS_NS || HAS_SL) && A.tile_fluid != nullptr && A.tile_fluid[c * wp.bands + band] != 0)
+        wave_tile<MODEL, K, false, false, IRREG, false>(A, g, wp, band, c);
     else
-        wave_tile<MODEL, K, HAS_NS, HAS_SL, IRREG>(A, g, wp, band, c);
+        wave_tile<MODEL, K, HAS_NS, HAS_SL, IRREG, false>(A, g, wp, band, c);
 }
 
 // tile_fluid[c * bands + band] = 1 when no solid site lies in the tile's input window (same geometry as wave_tile).
-template <bool IRREG>
+// (MODEL only makes the instantiation unique to the translation unit that launches it)
+template <int MODEL, bool IRREG>
 __global__ void __launch_bounds__(32) tile_fluid_kernel(const uint32_t* __restrict__ ns, const uint32_t* __restrict__ sl,
                                                         const Geom g, const WavePlan wp, const int K, uint8_t* __restrict__ out)
 {
@@ -470,7 +479,7 @@ static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
     for (int cr = 2 * k; cr <= rows + 1; cr += 2) {
         const int    chunks = (rows + cr - 1) / cr;
         if (chunks + 2 > 65535) continue; // chunks ride in gridDim.y
-        const double w      = (double)chunks * wp.bands / 148.0; // warps per SM
+        const double w      = (double)chunks * wp.bands / (double)(h->sm_count > 0 ? h->sm_count : 148); // warps per SM
         const double rounds = fmax(1.0, ceil(w / resident));
         const double eff    = pow(fmin(1.0, (w / rounds) / resident), 0.6);
         const double cost   = (double)(cr + k - 1 + 3) * (rounds + 0.15) / eff;
@@ -498,6 +507,7 @@ static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
     return wp;
 }
 
+#if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 0
 bool wave_supported(const lgca_b200_lattice* h, int k)
 {
     if (k < 1 || k > (rule_of(h->cfg.model) == MODEL_HPP ? LGCA_MAX_K : LGCA_MAX_K_FHP)) return false;
@@ -508,6 +518,7 @@ bool wave_supported(const lgca_b200_lattice* h, int k)
     if (!h->g.wrap_y && (uint32_t)k > h->g.halo) return false;
     return true;
 }
+#endif
 
 template <int MODEL, int K, bool NS, bool SL, bool IRREG>
 static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s)
@@ -529,7 +540,7 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
                 h->tile_fluid_cap[K] = need;
             }
             if (p.chunks > 65535) return set_error(LGCA_B200_EINVAL, "chunk plan exceeds gridDim.y (%d chunks)", p.chunks);
-            tile_fluid_kernel<IRREG><<<dim3(p.bands, p.chunks, 1), dim3(32, 1, 1), 0, h->s_compute>>>(h->ns, h->sl, h->g, p, K,
+            tile_fluid_kernel<MODEL, IRREG><<<dim3(p.bands, p.chunks, 1), dim3(32, 1, 1), 0, h->s_compute>>>(h->ns, h->sl, h->g, p, K,
                                                                                               h->tile_fluid[K]);
             h->launches++;
             LGCA_CUDA_CHECK(cudaGetLastError());
@@ -549,7 +560,12 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
     A.mul_two = 2u; A.mul_half = 0x80000000u;
     A.stride_bytes = (uint32_t)(h->g.plane_stride * sizeof(uint32_t));
     A.tile_fluid = (NS || SL) ? h->tile_fluid[K] : nullptr;
-    if (!in) return 0; // prepare only (wave_prepare): plan + module load, no launch
+    if (!in) { // prepare only (wave_prepare): plan + module load, no launch.  The flag kernel too: a plan may be
+               // re-made (mask upload) after the ring has started, and a lazy module load behind a spinning kernel can hang
+        cudaFuncAttributes fa;
+        LGCA_CUDA_CHECK(cudaFuncGetAttributes(&fa, tile_fluid_kernel<MODEL, IRREG>));
+        return 0;
+    }
     if (wp.chunks > 65535) return set_error(LGCA_B200_EINVAL, "chunk plan exceeds gridDim.y (%d chunks)", wp.chunks);
     kernel<<<dim3(wp.bands, wp.chunks, 1), dim3(32, 1, 1), 0, s>>>(A, h->g, wp);
     h->launches++;
@@ -557,40 +573,68 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
     return 0;
 }
 
-template <int MODEL, int K>
+template <int MODEL, int K, bool IRREG>
 static int launch_mk(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s)
 {
-    if ((uint64_t)h->g.rows * h->g.pitch > 0xFFFFFFFFull || (uint64_t)h->g.plane_stride * sizeof(uint32_t) > 0xFFFFFFFFull)
-        return set_error(LGCA_B200_EINVAL, "plane too large for 32-bit word offsets");
-    const bool irreg = h->g.rem != 0;
-#define GO(NS, SL) (irreg ? launch_variant<MODEL, K, NS, SL, true>(h, in, out, s) : launch_variant<MODEL, K, NS, SL, false>(h, in, out, s))
+#define GO(NS, SL) launch_variant<MODEL, K, NS, SL, IRREG>(h, in, out, s)
     if (h->has_sl) return h->has_ns ? GO(true, true) : GO(false, true);
     return h->has_ns ? GO(true, false) : GO(false, false);
 #undef GO
 }
 
-template <int MODEL>
+template <int MODEL, bool IRREG>
 static int launch_m(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s)
 {
     switch (k) {
-    case 1: return launch_mk<MODEL, 1>(h, in, out, s);
-    case 2: return launch_mk<MODEL, 2>(h, in, out, s);
-    case 3: return launch_mk<MODEL, 3>(h, in, out, s);
-    case 4: return launch_mk<MODEL, 4>(h, in, out, s);
-    case 5: return launch_mk<MODEL, 5>(h, in, out, s);
-    case 6: return launch_mk<MODEL, 6>(h, in, out, s);
-    case 7: if (MODEL == MODEL_HPP) return launch_mk<MODEL_HPP, 7>(h, in, out, s); break;
-    case 8: if (MODEL == MODEL_HPP) return launch_mk<MODEL_HPP, 8>(h, in, out, s); break;
+    case 1: return launch_mk<MODEL, 1, IRREG>(h, in, out, s);
+    case 2: return launch_mk<MODEL, 2, IRREG>(h, in, out, s);
+    case 3: return launch_mk<MODEL, 3, IRREG>(h, in, out, s);
+    case 4: return launch_mk<MODEL, 4, IRREG>(h, in, out, s);
+    case 5: return launch_mk<MODEL, 5, IRREG>(h, in, out, s);
+    case 6: return launch_mk<MODEL, 6, IRREG>(h, in, out, s);
+    case 7: if (MODEL == MODEL_HPP) return launch_mk<MODEL_HPP, 7, IRREG>(h, in, out, s); break;
+    case 8: if (MODEL == MODEL_HPP) return launch_mk<MODEL_HPP, 8, IRREG>(h, in, out, s); break;
     }
     return set_error(LGCA_B200_EINVAL, "unsupported k_fuse %d", k);
 }
 
+// The kernel variants are spread over six translation units (collision rule x regular/irregular width) that the
+// build compiles in parallel: -DLGCA_WAVE_TU=0..5 selects one, no define = everything in one unit.
+int launch_wave_hpp_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
+int launch_wave_hpp_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
+int launch_wave_fhp1_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
+int launch_wave_fhp1_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
+int launch_wave_fhp2_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
+int launch_wave_fhp2_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
+#if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 0
+int launch_wave_hpp_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s) { return launch_m<MODEL_HPP, false>(h, in, out, k, s); }
+#endif
+#if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 1
+int launch_wave_hpp_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s) { return launch_m<MODEL_HPP, true>(h, in, out, k, s); }
+#endif
+#if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 2
+int launch_wave_fhp1_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s) { return launch_m<MODEL_FHP_I, false>(h, in, out, k, s); }
+#endif
+#if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 3
+int launch_wave_fhp1_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s) { return launch_m<MODEL_FHP_I, true>(h, in, out, k, s); }
+#endif
+#if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 4
+int launch_wave_fhp2_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s) { return launch_m<MODEL_FHP_II, false>(h, in, out, k, s); }
+#endif
+#if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 5
+int launch_wave_fhp2_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s) { return launch_m<MODEL_FHP_II, true>(h, in, out, k, s); }
+#endif
+
+#if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 0
 int launch_step_wave(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s)
 {
+    if ((uint64_t)h->g.rows * h->g.pitch > 0xFFFFFFFFull || (uint64_t)h->g.plane_stride * sizeof(uint32_t) > 0xFFFFFFFFull)
+        return set_error(LGCA_B200_EINVAL, "plane too large for 32-bit word offsets");
+    const bool irreg = h->g.rem != 0;
     switch (rule_of(h->cfg.model)) {
-    case MODEL_HPP:   return launch_m<MODEL_HPP>(h, in, out, k, s);
-    case MODEL_FHP_I: return launch_m<MODEL_FHP_I>(h, in, out, k, s);
-    default:          return launch_m<MODEL_FHP_II>(h, in, out, k, s);
+    case MODEL_HPP:   return irreg ? launch_wave_hpp_irr(h, in, out, k, s) : launch_wave_hpp_reg(h, in, out, k, s);
+    case MODEL_FHP_I: return irreg ? launch_wave_fhp1_irr(h, in, out, k, s) : launch_wave_fhp1_reg(h, in, out, k, s);
+    default:          return irreg ? launch_wave_fhp2_irr(h, in, out, k, s) : launch_wave_fhp2_reg(h, in, out, k, s);
     }
 }
 
@@ -599,6 +643,11 @@ bool wave_has_edge_chunks(lgca_b200_lattice* h, int k)
 {
     if (!wave_supported(h, k)) return false;
     if (!h->plan_valid[k] && launch_step_wave(h, nullptr, nullptr, k, 0) != 0) return false;
+    // The spinning edge tiles are scheduled first.  If they alone could fill the resident-block capacity of the device,
+    // the push kernel of the previous block (which the NEIGHBOUR's edge tiles wait for) might never be dispatched and
+    // the ring would hang: very wide strips fall back to the stream-ordered wait kernel.
+    const int sms = h->sm_count > 0 ? h->sm_count : 148;
+    if (2 * h->plans[k].bands > 4 * sms) return false;
     return h->plans[k].edge_rows > 0;
 }
 
@@ -607,10 +656,6 @@ bool wave_has_edge_chunks(lgca_b200_lattice* h, int k)
 // same process is spinning in the ring's wait kernel; the ring calls this before it starts.
 int wave_prepare(lgca_b200_lattice* h)
 {
-    // the flag kernel too: a plan may be re-made (mask upload) after the ring has started
-    cudaFuncAttributes fa;
-    LGCA_CUDA_CHECK(cudaFuncGetAttributes(&fa, tile_fluid_kernel<false>));
-    LGCA_CUDA_CHECK(cudaFuncGetAttributes(&fa, tile_fluid_kernel<true>));
     for (int k = 1; k <= h->k_fuse; ++k) {
         if (!wave_supported(h, k)) continue;
         const int rc = launch_step_wave(h, nullptr, nullptr, k, 0);
@@ -618,5 +663,6 @@ int wave_prepare(lgca_b200_lattice* h)
     }
     return 0;
 }
+#endif // LGCA_WAVE_TU == 0
 
 } // namespace lgca_b200

@@ -6,7 +6,7 @@
 // viewers (apps/pipe/pipe_viewer.cpp:100-184):
 //     mean velocity -> (body force) -> PP_INTERVAL x collide_and_propagate -> snapshot -> post_process [-> write]
 // Flags follow src/utils.h:49-83 (-r/--Re, -m/--Ma, -d/--n-dir, -s/--steps, -c/--cg-radius, -w/--write-steps,
-// --device, -o/--output) plus --model, --pp-interval, --dims, --k-fuse, --hash-every, --no-cell-fields, --quiet.
+// --device, -o/--output) plus --gpus / --devices (row strips over several GPUs), --model, --pp-interval, --dims, --k-fuse, --hash-every, --no-cell-fields, --quiet.
 #include <fcntl.h>
 #include <unistd.h>
 
@@ -29,7 +29,8 @@ struct Args {
     std::string test_case = LGCA_APP_CASE;
     std::string model;
     Real        Re = 80.0, Ma = 0.3;
-    int         steps = 50, cg = 10, write_steps = 0, pp_interval = 5, device = 0, k_fuse = 0;
+    int         steps = 50, cg = 10, write_steps = 0, pp_interval = 5, device = 0, k_fuse = 0, gpus = 1;
+    std::vector<int> devices;
     int         hash_every = 0;
     unsigned    dim_x = 0, dim_y = 0;
     bool        cell_fields = true, quiet = false, bc_forward = false;
@@ -46,7 +47,8 @@ uint64_t fnv1a64(const uint8_t* p, size_t n)
 void usage(const char* argv0)
 {
     printf("usage: %s [-r Re] [-m Ma] [-d 4|6|7] [--model HPP|FHP_I|FHP_II|FHP_III] [-s steps] [-c cg-radius]\n"
-           "          [-w write-steps] [--pp-interval n] [--dims X Y] [--device n] [--k-fuse k] [-o none|vti] [--out-dir d]\n"
+           "          [-w write-steps] [--pp-interval n] [--dims X Y] [--device n] [--gpus n | --devices a,b,..] [--k-fuse k]\n"
+           "          [-o none|vti|png] [--out-dir d]\n"
            "          [--hash-every n] [--bounce forward|back] [--no-cell-fields] [--quiet]\n", argv0);
 }
 
@@ -74,6 +76,18 @@ bool parse(int argc, char** argv, Args& a)
         else if (f == "--pp-interval") a.pp_interval = atoi(next("pp-interval"));
         else if (f == "--dims") { a.dim_x = (unsigned)atoi(next("dims")); a.dim_y = (unsigned)atoi(next("dims")); }
         else if (f == "--device") a.device = atoi(next("device"));
+        else if (f == "--gpus") a.gpus = atoi(next("gpus"));
+        else if (f == "--devices") { // explicit ordinals of the strips, e.g. 0,1,2,3 (a device may repeat: testing)
+            std::string v = next("devices");
+            a.devices.clear();
+            for (size_t p0 = 0; p0 <= v.size();) {
+                size_t p1 = v.find(',', p0);
+                if (p1 == std::string::npos) p1 = v.size();
+                if (p1 > p0) a.devices.push_back(atoi(v.substr(p0, p1 - p0).c_str()));
+                p0 = p1 + 1;
+            }
+            a.gpus = (int)a.devices.size();
+        }
         else if (f == "--k-fuse") a.k_fuse = atoi(next("k-fuse"));
         else if (f == "-o" || f == "--output") a.output = next("output");
         else if (f == "--out-dir") a.out_dir = next("out-dir");
@@ -94,6 +108,8 @@ int run(const Args& a)
 {
     B200Options opt;
     opt.device = a.device;
+    opt.n_gpus = a.gpus;
+    opt.devices = a.devices;
     opt.k_fuse = a.k_fuse;
     opt.cell_fields = a.cell_fields;
     // --quiet: the base-class ctor prints the parameter banner; silence fd 1 around the construction only

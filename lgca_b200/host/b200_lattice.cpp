@@ -52,7 +52,7 @@ B200_Lattice<model_>::B200_Lattice(const string test_case, unsigned int dim_x, u
 template <Model model_>
 B200_Lattice<model_>::~B200_Lattice()
 {
-    if (m_h) lgca_b200_destroy(m_h);
+    if (m_h) lgca_b200_group_destroy(m_h);
     free_memory();
 }
 
@@ -106,7 +106,15 @@ void B200_Lattice<model_>::create_device_lattice()
     cfg.device = m_opt.device;
     cfg.k_fuse = m_opt.k_fuse;
     cfg.flags  = m_opt.cell_fields ? 0u : (uint32_t)LGCA_B200_FLAG_NO_CELL_FIELDS;
-    const int rc = lgca_b200_create(&cfg, &m_h);
+    if (m_opt.n_gpus < 1) m_opt.n_gpus = 1;
+    std::vector<int> devs = m_opt.devices;
+    if (devs.empty()) for (int i = 0; i < m_opt.n_gpus; ++i) devs.push_back(m_opt.device + i);
+    if ((int)devs.size() != m_opt.n_gpus) {
+        printf("ERROR in B200_Lattice::B200_Lattice(): %d device ordinals given for %d GPUs.\n", (int)devs.size(), m_opt.n_gpus);
+        fflush(stdout);
+        abort();
+    }
+    const int rc = lgca_b200_group_create(&cfg, m_opt.n_gpus, devs.data(), &m_h);
     if (rc) fail("B200_Lattice", rc);
 }
 
@@ -114,17 +122,17 @@ template <Model model_>
 void B200_Lattice<model_>::setup_parallel()
 {
     lgca_b200_info info;
-    const int rc = lgca_b200_get_info(m_h, &info);
+    const int rc = lgca_b200_group_get_info(m_h, &info);
     if (rc) fail("setup_parallel", rc);
-    printf("B200 configuration parameters: device %d, %u bit-planes of %u x %u words, %d fused steps per pass, "
-           "%.1f MB on the device.\n\n", m_opt.device, info.num_planes, info.y_rows, info.words_per_row, info.k_fuse,
-           info.device_bytes / 1.0e6);
+    printf("B200 configuration parameters: %d GPU(s)%s, %u bit-planes of %u x %u words, %d fused steps per pass, "
+           "%.1f MB on the device(s).\n\n", m_opt.n_gpus, m_opt.n_gpus > 1 ? " (row strips, peer-store halo ring)" : "",
+           info.num_planes, info.y_rows, info.words_per_row, info.k_fuse, info.device_bytes / 1.0e6);
 }
 
 template <Model model_>
 void B200_Lattice<model_>::copy_data_to_device()
 {
-    const int rc = lgca_b200_upload(m_h, this->m_node_state_cpu.ptr(), reinterpret_cast<const int32_t*>(this->m_cell_type_cpu),
+    const int rc = lgca_b200_group_upload(m_h, this->m_node_state_cpu.ptr(), reinterpret_cast<const int32_t*>(this->m_cell_type_cpu),
                                     this->m_rnd_cpu.ptr());
     if (rc) fail("copy_data_to_device", rc);
     m_on_device = true;
@@ -140,7 +148,7 @@ template <Model model_>
 void B200_Lattice<model_>::copy_data_from_device()
 {
     ensure_on_device();
-    const int rc = lgca_b200_download(m_h, this->m_node_state_cpu.ptr());
+    const int rc = lgca_b200_group_download(m_h, this->m_node_state_cpu.ptr());
     if (rc) fail("copy_data_from_device", rc);
 }
 
@@ -154,7 +162,7 @@ template <Model model_>
 void B200_Lattice<model_>::collide_and_propagate_n(int n_steps)
 {
     ensure_on_device();
-    const int rc = lgca_b200_step(m_h, n_steps);
+    const int rc = lgca_b200_group_step(m_h, n_steps);
     if (rc) fail("collide_and_propagate", rc);
 }
 
@@ -162,7 +170,7 @@ template <Model model_>
 void B200_Lattice<model_>::copy_data_to_output_buffer()
 {
     ensure_on_device();
-    const int rc = lgca_b200_snapshot(m_h);
+    const int rc = lgca_b200_group_snapshot(m_h);
     if (rc) fail("copy_data_to_output_buffer", rc);
 }
 
@@ -172,7 +180,7 @@ void B200_Lattice<model_>::post_process()
     ensure_on_device();
     const bool coarse = this->m_num_coarse_cells > 0 && this->m_dim_x % (2 * this->m_coarse_graining_radius) == 0 &&
                         this->m_dim_x >= 4 * this->m_coarse_graining_radius;
-    const int rc = lgca_b200_post_process(m_h, this->m_cell_density_cpu, this->m_cell_momentum_cpu,
+    const int rc = lgca_b200_group_post_process(m_h, this->m_cell_density_cpu, this->m_cell_momentum_cpu,
                                           coarse ? this->m_mean_density_cpu : nullptr,
                                           coarse ? this->m_mean_momentum_cpu : nullptr, m_opt.exact_post ? 1 : 0);
     if (rc) fail("post_process", rc);
@@ -204,7 +212,7 @@ std::vector<Real> B200_Lattice<model_>::get_mean_velocity()
     // no per-cell host fields (huge lattices): device reduction over the snapshot
     ensure_on_device();
     float out[2];
-    const int rc = lgca_b200_mean_velocity(m_h, out);
+    const int rc = lgca_b200_group_mean_velocity(m_h, out);
     if (rc) fail("get_mean_velocity", rc);
     mean_velocity[0] = out[0];
     mean_velocity[1] = out[1];
@@ -221,7 +229,7 @@ void B200_Lattice<model_>::apply_body_force(const int forcing)
     // call, so the stream position after the call equals the reference's as seen by this lattice.
     const size_t it_max = 2 * this->m_num_cells;
     size_t it = 0;
-    long   remaining = forcing;
+    long   remaining = (long)(unsigned int)forcing; // `unsigned int < int` compares as unsigned in the reference
     bool   first = true;
     std::vector<int32_t> batch;
     while ((first || remaining > 0) && it < it_max) {
@@ -231,7 +239,7 @@ void B200_Lattice<model_>::apply_body_force(const int forcing)
         batch.assign(m_draws.begin(), m_draws.begin() + want);
         size_t consumed = 0;
         uint32_t reverted = 0;
-        const int rc = lgca_b200_body_force(m_h, (int)remaining, batch.data(), want, &consumed, &reverted);
+        const int rc = lgca_b200_group_body_force(m_h, (int)remaining, batch.data(), want, &consumed, &reverted);
         if (rc) fail("apply_body_force", rc);
         m_draws.erase(m_draws.begin(), m_draws.begin() + consumed);
         it += consumed;
@@ -248,7 +256,7 @@ unsigned long B200_Lattice<model_>::get_n_particles()
 {
     if (!m_on_device) return Lattice<model_>::get_n_particles(); // still being set up on the host
     uint64_t n = 0;
-    const int rc = lgca_b200_count_particles(m_h, &n);
+    const int rc = lgca_b200_group_count_particles(m_h, &n);
     if (rc) fail("get_n_particles", rc);
     this->m_num_particles = n;
     return n;
@@ -257,7 +265,7 @@ unsigned long B200_Lattice<model_>::get_n_particles()
 template <Model model_>
 void B200_Lattice<model_>::synchronize()
 {
-    const int rc = lgca_b200_sync(m_h);
+    const int rc = lgca_b200_group_sync(m_h);
     if (rc) fail("synchronize", rc);
 }
 
@@ -266,7 +274,7 @@ double B200_Lattice<model_>::timed_steps(int n_steps)
 {
     ensure_on_device();
     float ms = 0;
-    const int rc = lgca_b200_timed_steps(m_h, n_steps, &ms);
+    const int rc = lgca_b200_group_timed_steps(m_h, n_steps, &ms);
     if (rc) fail("timed_steps", rc);
     return ms;
 }

@@ -10,7 +10,9 @@
 //   * post_process() fills the same four host float arrays (stable pointers, like IoVti expects);
 //   * get_mean_velocity() is the reference's sequential float32 loop over those host fields (bit-exact);
 //   * apply_body_force() feeds the caller's rand() stream, in order, to the exact device body force;
-//   * errors print "ERROR in ..." and abort(), like the reference.
+//   * errors print "ERROR in ..." and abort(), like the reference;
+//   * B200Options::n_gpus > 1 spreads the lattice over several GPUs of the box (row strips + halo ring behind
+//     lgca_b200_group_*): same calls, same host arrays, identical results.
 #ifndef LGCA_B200_HOST_B200_LATTICE_H_
 #define LGCA_B200_HOST_B200_LATTICE_H_
 
@@ -18,12 +20,16 @@
 
 #include "lattice.h"
 
-struct lgca_b200_lattice;
+#include <vector>
+
+struct lgca_b200_group;
 
 namespace lgca {
 
 struct B200Options {
-    int  device  = 0;     // CUDA device ordinal
+    int  device  = 0;     // CUDA device ordinal (single GPU)
+    int  n_gpus  = 1;     // > 1: the lattice is cut into row strips over n_gpus devices of this box (halo ring over NVLink)
+    std::vector<int> devices;  // explicit device ordinals of the strips (default: device, device+1, ...)
     int  k_fuse  = 0;     // time steps fused per HBM pass (0 = library default)
     bool cell_fields = true;  // produce per-cell density/momentum in post_process (needs 12 B/cell host+device)
     bool exact_post  = true;  // reference summation order for the coarse momentum-y means
@@ -52,7 +58,8 @@ public:
 
     void   synchronize();
     double timed_steps(int n_steps);                      // device time [ms] of n updates (CUDA events)
-    lgca_b200_lattice* handle() { return m_h; }
+    lgca_b200_group* handle() { return m_h; }
+    int  n_gpus() const { return m_opt.n_gpus; }
 
 private:
     void allocate_memory();
@@ -62,7 +69,7 @@ private:
     void fail(const char* where, int rc);
 
     B200Options        m_opt;
-    lgca_b200_lattice* m_h = nullptr;
+    lgca_b200_group*   m_h = nullptr;     // one lattice on n_gpus devices (n_gpus == 1: a plain whole-lattice handle)
     bool               m_on_device = false;   // host mirrors have been uploaded
     bool               m_fields_valid = false;
     std::deque<int>    m_draws;               // rand() values drawn ahead for the body force, in stream order

@@ -77,6 +77,16 @@ class Ring:
         else:
             self.exchange(self.STATE)
 
+    def republish(self):
+        """Publish the edge rows again after the live state was changed in place (body force, upload, initialiser).
+        Collective: every rank calls it at the same point."""
+        if self.world == 1 or self.halo == 0:
+            return
+        if self.native:
+            self.e.ring_republish()
+        else:
+            self.exchange(self.STATE)
+
     def _buffers(self, what):
         if what not in self._bufs:
             n = self.e.halo_bytes(what)
@@ -120,25 +130,31 @@ class Ring:
             n -= k
 
 
-def ring_body_force(engine, forcing, draws, num_cells, model, bf_dir, combine, batch=None):
+def ring_body_force(engine, forcing, draws, num_cells, model, bf_dir, combine, batch=None, ring=None):
     """Exact body force on a lattice that is split into strips (reference: OMP_Lattice::apply_body_force,
     src/omp_lattice.cpp:254-346).  Every rank calls this with the SAME draws (the caller's rand() values in stream
     order): each strip gathers the bytes of the drawn cells (0xFF outside the strip), `combine(uint8 array)` returns
     the element-wise minimum over all strips (all-reduce MIN), the batch is replayed in draw order on the host
-    (identically on every rank) and each strip applies the changed cells it owns.
+    (identically on every rank) and each strip applies the changed cells it owns.  The apply may change edge rows
+    the neighbours hold copies of: pass `ring` (a Ring) to have them republished, or call ring.republish() yourself
+    before the next step.
     Returns (draws consumed, particles reverted)."""
     import numpy as np
     from .capi import body_force_replay
     draws = np.asarray(draws, np.int64)
-    pos, remaining, first, reverted = 0, int(forcing), True, 0
+    pos, remaining, first, reverted, changed = 0, int(forcing), True, 0, False
     while pos < draws.size and (first or remaining > 0):
         n = batch or max(4096, min(1 << 20, remaining * 12))
         cells = (draws[pos:pos + n] % num_cells).astype(np.int32)
         combined = combine(engine.body_force_gather(cells))
         used, rev, ch_cells, ch_bytes = body_force_replay(model, bf_dir, remaining if first else max(remaining, 1), cells, combined)
-        engine.body_force_apply(ch_cells, ch_bytes)
+        if ch_cells.size:
+            engine.body_force_apply(ch_cells, ch_bytes)
+            changed = True
         pos += used
         remaining -= rev
         reverted += rev
         first = False
+    if changed and ring is not None:
+        ring.republish()
     return pos, reverted

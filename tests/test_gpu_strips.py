@@ -45,6 +45,9 @@ class LocalRing:
     ("FHP_II", (512, 128), "reflecting_back", 4, 3),
     ("FHP_I", (300, 64), "reflecting_forward", 2, 1),
     ("HPP", (640, 90), "reflecting_forward", 3, 4),
+    # dim_x < 64: only the generic kernel applies, which writes owned rows only -> ONE step per exchange
+    ("FHP_III", (48, 64), "pipe", 2, 4),
+    ("HPP", (33, 30), "reflecting_back", 3, 2),
 ])
 def test_strips_equal_single_lattice(model, dims, bc, nstrips, k):
     import lgca_b200
@@ -69,7 +72,7 @@ def test_strips_equal_single_lattice(model, dims, bc, nstrips, k):
     halo = engines[0].halo_rows()
     assert halo >= k and halo % 2 == 0
     block = engines[0].steps_per_exchange()
-    assert block == k
+    assert block == (k if dims[0] >= 64 else 1)
     done = 0
     for n in (1, k, 2 * k + 1, 7):
         left = n
@@ -90,73 +93,135 @@ def test_strips_equal_single_lattice(model, dims, bc, nstrips, k):
         e.close()
 
 
-@pytest.mark.parametrize("model,dims,bc,nstrips,k", [
-    ("FHP_III", (256, 96), "karman", 2, 2),
-    ("FHP_III", (1024, 120), "periodic", 3, 4),
-    ("FHP_II", (512, 128), "reflecting_back", 4, 3),
-    ("HPP", (640, 96), "reflecting_forward", 3, 4),
-])
-def test_native_ring_equals_single_lattice(model, dims, bc, nstrips, k):
-    """Same invariance through the native ring: peer stores into the neighbours' ghost rows + epoch flags,
-    everything enqueued by lgca_b200_ring_step (strips of one process share plain device pointers)."""
+def make_strips(o, nstrips, k, cg=0, unit=2, **kw):
     import lgca_b200
     from lgca_b200.ring import partition_rows
-    o = Oracle(model, dims=dims, cg=1, rng=OracleRng(6))
-    o.apply_bc(bc)
-    o.init("random")
-    parts = partition_rows(dims[1], nstrips, 2)
-    assert len(set(r for _, r in parts)) == 1  # native ring needs equal strip heights
+    parts = partition_rows(o.dim_y, nstrips, unit)
     engines = []
     for y0, rows in parts:
-        e = lgca_b200.Engine(model, dims[0], dims[1], k_fuse=k, y_begin=y0, y_rows=rows)
-        sl = slice(y0 * dims[0], (y0 + rows) * dims[0])
+        e = lgca_b200.Engine(o.model, o.dim_x, o.dim_y, cg_radius=cg, k_fuse=k, y_begin=y0, y_rows=rows, **kw)
+        sl = slice(y0 * o.dim_x, (y0 + rows) * o.dim_x)
         e.upload(o.state[sl], o.cell_type[sl], o.rnd)
         engines.append(e)
+    # every strip runs with the union of the wall kinds; ghost rows get the neighbours' masks once
     flags = [e.wall_flags() for e in engines]
     for e in engines:
         e.set_wall_flags(any(f[0] for f in flags), any(f[1] for f in flags))
     LocalRing(engines).exchange(1)  # static masks of the ghost rows: once, through the packed-buffer path
+    return engines, parts
+
+
+def connect_native(engines):
     desc = [e.ring_export() for e in engines]
     n = len(engines)
     for r, e in enumerate(engines):
         e.ring_connect(desc[(r - 1) % n], desc[(r + 1) % n])
     for e in engines:
         e.ring_start()
+
+
+@pytest.mark.parametrize("model,dims,bc,nstrips,k", [
+    ("FHP_III", (256, 96), "karman", 2, 2),
+    ("FHP_III", (1024, 120), "periodic", 3, 4),
+    ("FHP_II", (512, 128), "reflecting_back", 4, 3),
+    ("HPP", (640, 96), "reflecting_forward", 3, 4),
+    ("FHP_III", (1024, 100), "pipe", 3, 4),        # strips of unequal height (34 / 34 / 32 rows)
+    ("FHP_I", (40, 48), "pipe", 2, 3),             # dim_x < 64: generic kernel, one step per exchange, wait kernel
+])
+def test_native_ring_equals_single_lattice(model, dims, bc, nstrips, k):
+    """Same invariance through the native ring: peer stores into the neighbours' ghost rows + epoch flags,
+    everything enqueued by lgca_b200_ring_step (strips of one process share plain device pointers).  Snapshots are
+    taken in between: the three plane sets of every strip rotate in lockstep (zero-copy snapshot)."""
+    o = Oracle(model, dims=dims, cg=1, rng=OracleRng(6))
+    o.apply_bc(bc)
+    o.init("random")
+    engines, parts = make_strips(o, nstrips, k)
+    connect_native(engines)
     done = 0
-    for steps in (1, k, 3 * k + 1, 10):
+    for i, steps in enumerate((1, k, 3 * k + 1, 10, 2)):
         for e in engines:
             e.ring_step(steps)
         o.step(steps)
         done += steps
+        if i % 2 == 1:
+            for e in engines:
+                e.snapshot()
         got = np.concatenate([e.download() for e in engines])
         assert np.array_equal(got, o.state), "after %d steps" % done
     for e in engines:
         e.close()
 
 
-def test_body_force_on_strips():
-    """Exact body force across strips: gather on every strip, combine (minimum), ordered host replay, apply."""
-    import lgca_b200
+@pytest.mark.parametrize("native", [False, True], ids=["packed", "native"])
+def test_strip_snapshots_and_coarse_means(native):
+    """Post-processing on strips: the coarse means of a strip's top coarse row reach one row into the upper neighbour
+    (reference window, src/omp_lattice.cpp:423-436).  Snapshot on every strip, step on, then post-process: the union of
+    the strips' fields equals the oracle's, and the snapshot is insulated from the stepping (zero-copy rotation)."""
+    cg = 4
+    o = Oracle("FHP_III", dims=(256, 96), cg=cg, rng=OracleRng(11))
+    o.apply_bc("karman")
+    o.init("random")
+    engines, parts = make_strips(o, 3, 4, cg=cg, unit=2 * cg)
+    ring = LocalRing(engines)
+    if native:
+        connect_native(engines)
+    else:
+        ring.exchange(0)
+
+    def advance(n):
+        block = engines[0].steps_per_exchange()
+        while n > 0:
+            b = min(n, block)
+            for e in engines:
+                e.ring_step(b) if native else e.step(b)
+            if not native:
+                ring.exchange(0)
+            n -= b
+
+    for rounds in range(3):
+        advance(7)
+        o.step(7)
+        for e in engines:
+            e.snapshot()
+        o.snapshot()
+        o.post_process()
+        advance(5)          # the snapshot must not see these
+        o.step(5)
+        fields = [e.post_process(cell=True, mean=True, exact=True) for e in engines]
+        for name in ("cell_density", "cell_momentum", "mean_density", "mean_momentum"):
+            got = np.concatenate([f[name] for f in fields])
+            assert np.array_equal(got, getattr(o, name)), (name, rounds)
+        got = np.concatenate([e.download() for e in engines])
+        assert np.array_equal(got, o.state)
+    for e in engines:
+        e.close()
+
+
+@pytest.mark.parametrize("native", [False, True], ids=["packed", "native"])
+def test_body_force_on_strips(native):
+    """Exact body force across strips: gather on every strip, combine (minimum), ordered host replay, apply --
+    then the changed edge rows are published again and the lattice steps on: the next steps read the neighbours'
+    ghost rows, so a stale copy would show up here (force -> step -> compare)."""
     from lgca_b200.capi import body_force_replay
-    from lgca_b200.ring import partition_rows
     model, dims, nstrips = "FHP_III", (256, 96), 3
     o = Oracle(model, dims=dims, cg=1, bf_dir=b"x", rng=OracleRng(8))
     o.apply_bc("karman")
     o.init("random")
-    parts = partition_rows(dims[1], nstrips, 2)
-    engines = []
-    for y0, rows in parts:
-        e = lgca_b200.Engine(model, dims[0], dims[1], bf_dir="x", k_fuse=2, y_begin=y0, y_rows=rows)
-        sl = slice(y0 * dims[0], (y0 + rows) * dims[0])
-        e.upload(o.state[sl], o.cell_type[sl], o.rnd)
-        engines.append(e)
+    engines, parts = make_strips(o, nstrips, 2, bf_dir="x")
+    ring = LocalRing(engines)
+    if native:
+        connect_native(engines)
+    else:
+        ring.exchange(0)
     o.rng = OracleRng(123)
     g = OracleRng(123)
     pending = []
     n = o.num_cells
     for forcing in (0, 3, 200, 1500):
+        for e in engines:
+            e.snapshot()           # the canonical schedule snapshots before the force: copy-on-write on every strip
         used_o, rev_o = o.body_force(forcing)
-        remaining, first, used_t, rev_t = forcing, True, 0, 0
+        remaining, first, used_t, rev_t, changed = forcing, True, 0, 0, False
         while first or remaining > 0:
             want = max(512, remaining * 6)
             while len(pending) < want:
@@ -166,8 +231,10 @@ def test_body_force_on_strips():
             for e in engines:
                 combined = np.minimum(combined, e.body_force_gather(cells))
             used, rev, cc, cb = body_force_replay(model, "x", remaining if first else max(remaining, 1), cells, combined)
-            for e in engines:
-                e.body_force_apply(cc, cb)
+            if cc.size:
+                for e in engines:
+                    e.body_force_apply(cc, cb)
+                changed = True
             del pending[:used]
             used_t += used
             rev_t += rev
@@ -176,5 +243,33 @@ def test_body_force_on_strips():
         assert (used_t, rev_t) == (used_o, rev_o)
         got = np.concatenate([e.download() for e in engines])
         assert np.array_equal(got, o.state), forcing
+        if changed:                # mandatory after an in-place write: publish the edge rows again
+            if native:
+                for e in engines:
+                    e.ring_republish()
+            else:
+                ring.exchange(0)
+        for steps in (2, 1):
+            for e in engines:
+                e.ring_step(steps) if native else e.step(steps)
+            if not native:
+                ring.exchange(0)
+            o.step(steps)
+        got = np.concatenate([e.download() for e in engines])
+        assert np.array_equal(got, o.state), "stepping after forcing %d" % forcing
     for e in engines:
         e.close()
+
+
+def test_strip_geometry_is_validated():
+    """Strips shorter than their halo, FHP strips on odd rows: rejected at create (LGCA_B200_EINVAL)."""
+    import lgca_b200
+    with pytest.raises(lgca_b200.LgcaError):
+        lgca_b200.Engine("FHP_III", 256, 96, k_fuse=6, y_begin=0, y_rows=4)      # 4 rows < halo 6
+    with pytest.raises(lgca_b200.LgcaError):
+        lgca_b200.Engine("FHP_III", 256, 96, k_fuse=2, y_begin=3, y_rows=32)     # odd first row on a hex lattice
+    with pytest.raises(lgca_b200.LgcaError):
+        lgca_b200.Engine("FHP_II", 256, 96, k_fuse=2, y_begin=32, y_rows=33)     # odd height
+    e = lgca_b200.Engine("HPP", 256, 96, k_fuse=2, y_begin=3, y_rows=33)         # HPP has no row parity
+    assert e.steps_per_exchange() == 1                                           # ... but then only the generic kernel applies
+    e.close()

@@ -16,6 +16,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "lgca_b200", "host", "bin")
 GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "appendix_b.json")))
+REF_RUNS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_runs.json")))
 
 
 @pytest.fixture(scope="module")
@@ -71,6 +72,41 @@ def test_pipe_fhp3_default(apps):
     h = hashes(p.stdout)
     for s in (0, 100, 500):
         assert h[s] == case["hashes"][str(s)]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices", [None, "0,0"], ids=["1gpu", "2strips"])
+def test_karman_app_default_1000_steps(apps, devices):
+    """The north-star target through the C++ drop-in: lgca-karman at the app's defaults (FHP-III 4400 x 2200), driven by
+    the process's real glibc rand() stream, 1000 steps on the canonical schedule -- state hashes equal to the
+    unmodified reference's (tests/golden/reference_runs.json).  `--devices 0,0` runs it as two row strips behind the
+    same B200_Lattice (B200Options::n_gpus; both strips on device 0 where the box has one GPU)."""
+    gold = REF_RUNS["karman_default"]
+    extra = ["--devices", devices] if devices else []
+    p = run_app("lgca-karman", "--steps", 1000, "--hash-every", 500, "--quiet", *extra)
+    h = hashes(p.stdout)
+    for s in (0, 500, 1000):
+        assert h[s] == gold["hashes"][str(s)], s
+    assert "Error check PASSED" in p.stdout
+
+
+@pytest.mark.gpu
+def test_apps_on_several_strips(apps):
+    """--gpus / --devices: every app gives the single-GPU hashes on row strips (C1 pipe incl. strip body force)."""
+    case = [c for c in GOLD["b3_pipe_schedule"] if c["model"] == "FHP_I"][0]
+    p = run_app("lgca-pipe", "--model", "FHP_I", "--steps", 500, "--hash-every", 500, "--quiet", "--devices", "0,0,0")
+    assert hashes(p.stdout)[500] == case["hashes"]["500"]
+    case = GOLD["b2_pure_stepping"][1]
+    p = run_app("lgca-box", "-r", 255, "-c", 16, "--model", "FHP_II", "--steps", 200, "--pp-interval", 10, "--hash-every", 100,
+                "--quiet", "--devices", "0,0,0,0")
+    h = hashes(p.stdout)
+    for s in (0, 100, 200):
+        assert h[s] == case["hashes"][str(s)]
+    import lgca_b200
+    if lgca_b200.load_library().lgca_b200_device_count() >= 2:
+        p = run_app("lgca-box", "-r", 255, "-c", 16, "--model", "FHP_II", "--steps", 200, "--pp-interval", 10, "--hash-every", 100,
+                    "--quiet", "--gpus", 2)
+        assert hashes(p.stdout)[200] == case["hashes"]["200"]
 
 
 @pytest.mark.gpu

@@ -246,3 +246,54 @@ def test_oracle_body_force_directions(model, bf):
         o.body_force(forcing)
         assert np.array_equal(o.state, r.state)
     r.close()
+
+
+# ---- tests/golden/reference_runs.json: known answers generated from the UNMODIFIED reference at app-default and
+# config sizes (scripts/gen_golden_reference.py).  The oracle must reproduce them; the GPU tests then compare with them.
+REF_RUNS = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_runs.json")))
+
+
+@pytest.mark.parametrize("name,bc,upto", [("pipe_default_fhp3", "pipe", 100), ("karman_default", "karman", 5)])
+def test_oracle_reproduces_reference_app_runs(name, bc, upto):
+    """Canonical tick schedule at the apps' default sizes: ctor sizing, chirality field, BC painter, init_random, forcing
+    formulas, order-exact mean velocity, exact body force, stepping."""
+    gold = REF_RUNS[name]
+    o = Oracle(gold["model"], *gold["ctor"])
+    assert [o.dim_x, o.dim_y] == gold["dims"]
+    o.apply_bc(bc)
+    o.init("random")
+    assert fnv1a64(o.rnd) == gold["chirality_hash"] and fnv1a64(o.cell_type) == gold["cell_type_hash"]
+    assert o.hash() == gold["hashes"]["0"] and o.n_particles() == gold["particles"]
+    assert o.initial_forcing() == gold["initial_forcing"] and o.equilibrium_forcing() == gold["equilibrium_forcing"]
+    o.snapshot(); o.post_process()
+    forcing, done = o.initial_forcing(), 0
+    while done < upto:
+        mv = o.mean_velocity()
+        if str(done + 5) in gold["mv_at_tick_start"]:
+            assert [float(mv[0]), float(mv[1])] == gold["mv_at_tick_start"][str(done + 5)]
+        if mv[0] < np.float32(o.u):
+            if float(mv[0]) > 0.9 * o.u:
+                forcing = o.equilibrium_forcing()
+            o.body_force(forcing)
+        o.step(5)
+        done += 5
+        o.snapshot(); o.post_process()
+        if str(done) in gold["hashes"]:
+            assert o.hash() == gold["hashes"][str(done)], done
+
+
+def test_oracle_reproduces_reference_config_width_runs():
+    gold = REF_RUNS["hpp_4096"]
+    o = Oracle(gold["model"], *gold["ctor"])
+    o.apply_bc(gold["bc"]); o.init(gold["init"])
+    assert [o.dim_x, o.dim_y] == gold["dims"] and o.hash() == gold["hashes"]["0"]
+    o.step(1)
+    assert o.hash() == gold["hashes"]["1"]
+    o.step(12)
+    assert o.hash() == gold["hashes"]["13"] and o.n_particles() == gold["particles"]
+    gold = REF_RUNS["fhp3_32768x512"]
+    o = Oracle(gold["model"], dims=tuple(gold["dims"]), cg=gold["cg"])
+    o.apply_bc(gold["bc"]); o.init(gold["init"])
+    assert o.hash() == gold["hashes"]["0"] and fnv1a64(o.rnd) == gold["chirality_hash"]
+    o.step(13)
+    assert o.hash() == gold["hashes"]["13"]
