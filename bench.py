@@ -61,6 +61,34 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def kernel_source_stamp():
+    """Hash of the sources the fused-step kernel is compiled from: ncu traffic numbers in profiles/traffic.json are
+    only attached to a bench line when they were captured from exactly this kernel."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in ("lgca_step_wave.cu", "lgca_collide.cuh", "lgca_common.cuh", "lgca_internal.h"):
+        h.update(open(os.path.join(ROOT, "lgca_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(key):
+    """(bytes per launch, note) from profiles/traffic.json -- an ncu `--set full` capture of the same kernel build."""
+    tp = os.path.join(ROOT, "profiles", "traffic.json")
+    if not os.path.exists(tp):
+        return None, "no ncu capture under profiles/"
+    try:
+        t = json.load(open(tp))
+    except Exception as ex:
+        return None, "unreadable traffic.json: %r" % ex
+    ent = t.get("entries", {}).get(key)
+    if ent is None:
+        return None, "no ncu capture for %s" % key
+    if ent.get("kernel_stamp") != kernel_source_stamp():
+        return None, "stale: ncu capture %s was taken from kernel sources %s, this build is %s" % (
+            key, ent.get("kernel_stamp"), kernel_source_stamp())
+    return float(ent["dram_bytes_per_launch"]), "ncu dram__bytes_read.sum + dram__bytes_write.sum, capture %s" % ent.get("source", "?")
+
+
 class ClockSampler(threading.Thread):
     """Samples SM clock, power and throttle reasons DURING the timed region (NVML, 20 ms period)."""
 
@@ -246,6 +274,65 @@ def info_y_begin(e):
     return int(e.info().y_begin)
 
 
+def multi_gpu_parity(rank, world, local_rank, device, k_fuse, native):
+    """Decomposition invariance on PHYSICAL GPUs, inside the bench run: a small global lattice (FHP-III 8192 x 2048*N,
+    device counter-hash init keyed on the global cell) is advanced 13*k+1 steps as N row strips through the halo ring --
+    once all fluid, once with the Karman walls + cylinder, with snapshots in between (the strips' plane sets rotate) --
+    and rank 0 advances the same lattice as ONE whole lattice on its GPU.  Every strip's bytes must equal the matching
+    rows of the single-GPU result (blake2b digests, all-gathered).  Returns the report; the caller fails the run on a
+    mismatch."""
+    import hashlib
+    import torch.distributed as dist
+    import lgca_b200
+    from lgca_b200.ring import Ring, partition_rows
+    dx, rows, cg = 8192, 2048, 16
+    dim_y = rows * world
+    report = {"ok": True, "lattice": [dx, dim_y], "variants": []}
+    for bc in ("periodic", "karman"):
+        y0, yr = partition_rows(dim_y, world, 2 * cg)[rank]
+        e = lgca_b200.Engine("FHP_III", dx, dim_y, cg_radius=cg, device=local_rank, k_fuse=k_fuse, y_begin=y0, y_rows=yr,
+                             flags=lgca_b200.capi.FLAG_NO_CELL_FIELDS)
+        e.apply_bc_device(bc)
+        e.init_random_device(seed=7)
+        ring = Ring(e, rank, world, device=device, native=native)
+        ring.start()
+        k = e.steps_per_exchange()
+        steps = 13 * k + 1
+        ring.step(5 * k)
+        e.snapshot()
+        ring.step(steps - 5 * k)
+        e.snapshot()
+        mine = hashlib.blake2b(e.download().tobytes(), digest_size=16).hexdigest()
+        particles = e.count_particles()
+        e.sync()
+        dist.barrier()
+        e.ring_disconnect()    # every rank drops its mappings of the neighbours' memory before anyone frees it
+        dist.barrier()
+        e.close()
+        digests = [None] * world
+        dist.all_gather_object(digests, (mine, particles))
+        if rank == 0:
+            one = lgca_b200.Engine("FHP_III", dx, dim_y, cg_radius=cg, device=local_rank, k_fuse=k_fuse,
+                                   flags=lgca_b200.capi.FLAG_NO_CELL_FIELDS)
+            one.apply_bc_device(bc)
+            one.init_random_device(seed=7)
+            one.step(steps)
+            whole = one.download()
+            want_particles = one.count_particles()
+            one.close()
+            parts = partition_rows(dim_y, world, 2 * cg)
+            want = [hashlib.blake2b(whole[a * dx:(a + n) * dx].tobytes(), digest_size=16).hexdigest() for a, n in parts]
+            ok = [d[0] for d in digests] == want and sum(d[1] for d in digests) == want_particles
+            report["variants"].append({"bc": bc, "steps": steps, "k_fuse": k, "ok": bool(ok),
+                                       "digest": hashlib.blake2b(whole.tobytes(), digest_size=16).hexdigest(),
+                                       "strips_equal": [a == b for a, b in zip([d[0] for d in digests], want)]})
+            report["ok"] = report["ok"] and bool(ok)
+    flag = [report["ok"] if rank == 0 else None]
+    dist.broadcast_object_list(flag, src=0)
+    report["ok"] = bool(flag[0])
+    return report
+
+
 def run_b200_arm(args):
     import torch
     import torch.distributed as dist
@@ -269,6 +356,15 @@ def run_b200_arm(args):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=device)
+
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = multi_gpu_parity(rank, world, local_rank, device, args.k_fuse, native=not args.nccl_halo)
+        if not parity["ok"]:
+            if rank == 0:
+                print(json.dumps({"multi_gpu_parity": parity, "error": "row strips over %d GPUs differ from the single-GPU result" % world}))
+            dist.destroy_process_group()
+            return 3
 
     model, dx, rows, bc, cg, desc = WORKLOADS[args.workload]
     strong = args.workload in STRONG
@@ -331,12 +427,14 @@ def run_b200_arm(args):
     e2e_steps = max(1, min(args.steps, 3))
     barrier()
     t0 = time.perf_counter()
+    t_up = t_down = 0.0
     for _ in range(e2e_steps):
+        ta = time.perf_counter()
         e.upload(state=host_state.array)             # copy_data_to_device()
-        if world > 1:
-            e.sync()
-            dist.barrier()                           # every strip uploaded before anyone pushes ghost rows
-            ring.start()                             # ghost rows of the freshly uploaded strips
+        t_up += time.perf_counter() - ta
+        # ghost rows of the freshly uploaded strips: stream-ordered republish (the neighbours acknowledge on the
+        # device that they no longer read the old rows) -- no host barrier, ranks drift freely
+        ring.republish()
         ring.step(UPDATES_PER_STEP)                  # 100 x collide_and_propagate()
         e.snapshot()                                 # copy_data_to_output_buffer()
         if writer:
@@ -344,11 +442,21 @@ def run_b200_arm(args):
         e.post_process(cell=False, mean=True, exact=False, out=coarse)  # post_process() -> host coarse fields
         if writer:
             writer.submit(0, coarse)                 # IoVti::write of the coarse fields
+        ta = time.perf_counter()
         e.download(host_state.array)                 # copy_data_from_device()
+        t_down += time.perf_counter() - ta
     if writer:
         writer.drain()
     barrier()
     e2e_s = time.perf_counter() - t0
+    # per-rank PCIe rates of the two big copies (download includes waiting for the 100 updates to finish)
+    h2d_gbs = sites_rank * e2e_steps / max(t_up, 1e-9) / 1e9
+    if world > 1:
+        t = torch.tensor([h2d_gbs, -h2d_gbs], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        h2d_range = [float(t[0].item()), float(-t[1].item())]
+    else:
+        h2d_range = [h2d_gbs, h2d_gbs]
     if world > 1:
         t = torch.tensor([e2e_s], device=device)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -374,15 +482,9 @@ def run_b200_arm(args):
     alg_bytes = sites_rank * info.bytes_per_site_step_x8 / 8.0 * k
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (kms * 1e-3) / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tp):
-        try:
-            traffic = json.load(open(tp)).get("%s_k%d" % (args.workload, k))
-        except Exception:
-            traffic = None
+    traffic, traffic_note = measured_traffic("%s_k%d" % (args.workload, k))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "kernel": "step_wave_kernel<FHP_II rule, K=%d>" % k,
+                "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "traffic_source": traffic_note, "kernel": "step_wave_kernel<FHP_II rule, K=%d>" % k,
                 "launch_ms": kms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "dram_frac": (traffic / (kms * 1e-3) / 1e9 / peak) if traffic else None,
                 "limiter": "integer pipe + issue slots (LOP3/SHF/SHFL; sm__pipe_alu and issue_active in profiles/), not DRAM: dram_frac is the share of the copy peak the kernel really moves",
@@ -411,11 +513,15 @@ def run_b200_arm(args):
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "site updates/s", "h2d_bytes_per_step": sites_rank * world,
                     "d2h_bytes_per_step": (sites_rank + coarse_bytes) * world, "steps": e2e_steps,
-                    "path": "upload(pinned state bytes) -> 100 steps -> snapshot+post_process -> download"},
+                    "h2d_gbs_per_rank_min_max": h2d_range,
+                    "path": "upload(pinned state bytes) -> [strips: stream-ordered republish of the ghost rows, no barrier] -> "
+                            "100 steps -> snapshot+post_process -> download"},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "particles_conserved": bool(conserved),
         }
+        if parity is not None:
+            line["multi_gpu_parity"] = parity
     # ---- extras on rank 0 at N=1: CPU baseline and the Karman (C3) measurement ----------------------------
     if world == 1 and line is not None:
         if not args.no_cpu_baseline:
@@ -426,9 +532,15 @@ def run_b200_arm(args):
                 line["cpu_baseline"] = {"value": None, "unit": "site updates/s", "cores": os.cpu_count(), "kind": "unavailable",
                                         "sample": repr(ex)}
         if args.workload == "periodic" and not args.no_karman:
-            e.close()
+            teardown(e, world)
             line["karman"] = karman_extra(args, peak)
             line["diffusion_hpp"] = hpp_extra(args, peak)
+    if args.workload == "periodic" and not args.no_box:
+        # C4 at this N (all ranks take part); the main engine goes first: 65536 x 32768 needs the memory
+        teardown(e, world)
+        box = box_extra(args, rank, world, local_rank, device, peak)
+        if line is not None:
+            line["box"] = box
     if writer:
         writer.q.put(None)
         if writer.error:
@@ -439,10 +551,69 @@ def run_b200_arm(args):
         pass
     if line is not None:
         print(json.dumps(line))
-    e.close()
+    teardown(e, world)
     if world > 1:
         dist.destroy_process_group()
     return 0
+
+
+def teardown(e, world):
+    """Close a strip: every rank drops its mappings of the neighbours' memory before anyone frees it."""
+    if getattr(e, "h", None) is None:
+        return
+    e.sync()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        e.ring_disconnect()
+        dist.barrier()
+    e.close()
+
+
+def box_extra(args, rank, world, local_rank, device, peak):
+    """BASELINE config C4 (lgca-box FHP-II 65536 x 32768, bounce-back frame) cut into row strips over the N GPUs of the
+    run: STRONG scaling, device-timed (CUDA events on every rank's compute stream, max over ranks).  Attached to the
+    default line at every N, so the driver's 1/2/4/8 runs carry the C4 curve."""
+    import torch
+    import torch.distributed as dist
+    from lgca_b200.ring import Ring
+    model, dx, rows, bc, cg, desc = WORKLOADS["box"]
+    e = build_engine("box", rank, world, local_rank, args.k_fuse)
+    ring = Ring(e, rank, world, device=device, native=not args.nccl_halo)
+    ring.start()
+    k = e.steps_per_exchange() if world > 1 else e.info().k_fuse
+    n0 = e.count_particles()
+    stream = torch.cuda.ExternalStream(e.compute_stream(), device=device)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ring.step(4 * k)
+    best = None
+    for _ in range(3):
+        e.sync()
+        if world > 1:
+            dist.barrier()
+        ev0.record(stream)
+        ring.step(10 * k)
+        ev1.record(stream)
+        e.sync()
+        ms = ev0.elapsed_time(ev1)
+        if world > 1:
+            t = torch.tensor([ms], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        best = ms if best is None else min(best, ms)
+    n1 = e.count_particles()
+    if world > 1:
+        t = torch.tensor([n0, n1], device=device, dtype=torch.int64)
+        dist.all_reduce(t)
+        n0, n1 = int(t[0].item()), int(t[1].item())
+    info = e.info()
+    value = dx * rows * 10 * k / (best * 1e-3)
+    alg = value * info.bytes_per_site_step_x8 / 8.0 / 1e9
+    teardown(e, world)
+    return {"workload": desc, "value": value, "unit": "site updates/s", "n_gpus": world, "scaling": "strong",
+            "per_gpu": value / world, "k_fuse": k, "us_per_update": best * 1e3 / (10 * k), "rows_per_gpu": rows // world,
+            "roofline_achieved_gbs_per_gpu": alg / world, "roofline_frac_per_gpu": alg / world / peak,
+            "particles_conserved": bool(n0 == n1)}
 
 
 def karman_extra(args, peak):
@@ -493,6 +664,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-karman", action="store_true")
     ap.add_argument("--no-vti", action="store_true", help="skip the .vti write of the coarse fields")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU decomposition-invariance check (N > 1)")
+    ap.add_argument("--no-box", action="store_true", help="skip the C4 box extra")
     ap.add_argument("--nccl-halo", action="store_true", help="move ghost rows with NCCL send/recv instead of the native peer-store ring")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -64,9 +64,15 @@ def full(src, dst, key=None):
         def tobytes(k):
             i = hdr.index(k); v = float(r[i].replace(",", "")); u = units[i].lower()
             return v * {"byte": 1, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}[u]
+        # stamped with the kernel sources the capture was taken from: bench.py attaches a number only to the same build
+        sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+        from bench import kernel_source_stamp
         tp = os.path.join(os.path.dirname(dst), "traffic.json")
         t = json.load(open(tp)) if os.path.exists(tp) else {}
-        t[key] = tobytes('dram__bytes_read.sum') + tobytes('dram__bytes_write.sum')
+        if "entries" not in t:
+            t = {"entries": {}}
+        t["entries"][key] = {"dram_bytes_per_launch": tobytes('dram__bytes_read.sum') + tobytes('dram__bytes_write.sum'),
+                             "kernel_stamp": kernel_source_stamp(), "source": os.path.basename(dst)}
         json.dump(t, open(tp, "w"), indent=1, sort_keys=True)
 
 
