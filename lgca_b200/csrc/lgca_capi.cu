@@ -239,7 +239,9 @@ int lgca_b200_create(const lgca_b200_config* cfg, lgca_b200_lattice** out)
         lgca_b200_destroy(h);
         return set_cuda_error(e, "stream/event creation", __FILE__, __LINE__);
     }
-    rc = launch_build_xedge(h, h->s_compute);
+    // the cudaMemset calls above ran in the default stream, which the handle's non-blocking streams do not wait for
+    if (cudaDeviceSynchronize() != cudaSuccess) rc = set_cuda_error(cudaGetLastError(), "sync", __FILE__, __LINE__);
+    if (!rc) rc = launch_build_xedge(h, h->s_compute);
     if (!rc && cudaStreamSynchronize(h->s_compute) != cudaSuccess) rc = set_cuda_error(cudaGetLastError(), "sync", __FILE__, __LINE__);
     if (rc) { lgca_b200_destroy(h); return rc; }
     // all-fluid, zero chirality, empty lattice is a valid starting point

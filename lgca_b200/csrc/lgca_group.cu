@@ -66,6 +66,11 @@ int exchange_masks(lgca_b200_group* g)
             cudaMemcpyPeer(from_upper[lo], g->strips[lo]->cfg.device, bottom[i], g->strips[i]->cfg.device, bytes) != cudaSuccess)
             rc = set_cuda_error(cudaGetLastError(), "cudaMemcpyPeer (mask halo)", __FILE__, __LINE__);
     }
+    // cudaMemcpyPeer may return before the copy has finished and is not ordered against the handles' non-blocking
+    // streams: drain every device before the imports read the buffers
+    for (size_t i = 0; i < n && !rc; ++i)
+        if (cudaSetDevice(g->strips[i]->cfg.device) != cudaSuccess || cudaDeviceSynchronize() != cudaSuccess)
+            rc = set_cuda_error(cudaGetLastError(), "cudaDeviceSynchronize (mask halo)", __FILE__, __LINE__);
     for (size_t i = 0; i < n && !rc; ++i) {
         if ((rc = lgca_b200_halo_import(g->strips[i], LGCA_B200_HALO_MASKS, from_upper[i], from_lower[i]))) break;
         rc = lgca_b200_sync(g->strips[i]);
@@ -131,7 +136,9 @@ int lgca_b200_group_create(const lgca_b200_config* cfg, int n_gpus, const int* d
     if (n_gpus < 1) return set_error(LGCA_B200_EINVAL, "n_gpus must be >= 1");
     const int ndev = lgca_b200_device_count();
     if (ndev == 0) return set_error(LGCA_B200_ENODEV, "no CUDA device: lgca_b200 has no CPU path");
-    if (n_gpus > ndev) return set_error(LGCA_B200_EINVAL, "%d GPUs requested, %d visible", n_gpus, ndev);
+    if (!dev_ids && n_gpus > ndev) return set_error(LGCA_B200_EINVAL, "%d GPUs requested, %d visible", n_gpus, ndev);
+    for (int i = 0; dev_ids && i < n_gpus; ++i) // an ordinal may repeat: several strips on one device (testing)
+        if (dev_ids[i] < 0 || dev_ids[i] >= ndev) return set_error(LGCA_B200_EINVAL, "device %d out of range (%d visible)", dev_ids[i], ndev);
     // strips: contiguous, heights multiples of `unit` rows (coarse cells stay strip-local, hex row parity stays global)
     const uint32_t unit = std::max<uint32_t>(2u * cfg->cg_radius, 2u);
     if (n_gpus > 1 && (cfg->dim_y % unit || cfg->dim_y / unit < (uint32_t)n_gpus))

@@ -163,6 +163,7 @@ int lgca_b200_ring_export(lgca_b200_lattice* h, void* descriptor, size_t bytes)
     if (!h->ring_flags) {
         LGCA_CUDA_CHECK(cudaMalloc(&h->ring_flags, 64));
         LGCA_CUDA_CHECK(cudaMemset(h->ring_flags, 0, 64));
+        LGCA_CUDA_CHECK(cudaDeviceSynchronize()); // default-stream memset vs. the non-blocking ring streams
         // highest priority: the tiny push/signal kernels must be dispatched ahead of the next step kernel's blocks,
         // which become ready at the same moment and would otherwise fill every SM first
         int prio_lo = 0, prio_hi = 0;

@@ -2,7 +2,7 @@
 # Round-2 GPU call A (1 GPU): full GPU test suite, smoke, short bench.  Artefacts -> gpurun_out/.
 TAG=${1:-r02a}
 mkdir -p gpurun_out
-( time timeout 1500 python -m pytest tests -m gpu -x -q ) > gpurun_out/${TAG}_tests.log 2>&1
+( time timeout 1500 python -m pytest tests -m gpu -q ) > gpurun_out/${TAG}_tests.log 2>&1
 echo "tests rc=$?" >> gpurun_out/${TAG}_tests.log
 tail -30 gpurun_out/${TAG}_tests.log
 timeout 120 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${TAG}_smoke.log 2>&1; tail -2 gpurun_out/${TAG}_smoke.log
