@@ -95,18 +95,29 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.samples, self.stop_flag, self.err = index, [], False, None
-
-    def run(self):
-        try:
+        self.nv = self.h = self.get_reasons = None
+        self.max_sm = None
+        try:  # NVML is initialised BEFORE the timed region: the region may be shorter than nvmlInit()
             import pynvml as nv
             nv.nvmlInit()
-            h = nv.nvmlDeviceGetHandleByIndex(self.index)
-            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
-            get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+            self.nv, self.h = nv, nv.nvmlDeviceGetHandleByIndex(index)
+            self.max_sm = nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM)
+            self.get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        except Exception as ex:  # pragma: no cover
+            self.err = repr(ex)
+
+    def sample(self):
+        nv, h = self.nv, self.h
+        self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
+                             int(self.get_reasons(h))))
+
+    def run(self):
+        if self.nv is None:
+            return
+        try:
             while not self.stop_flag:
-                self.samples.append((nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM), nv.nvmlDeviceGetPowerUsage(h) / 1000.0,
-                                     int(get_reasons(h))))
-                time.sleep(0.02)
+                self.sample()
+                time.sleep(0.005)
         except Exception as ex:  # pragma: no cover
             self.err = repr(ex)
 

@@ -59,3 +59,16 @@ def test_replay_matches_oracle(capi, model, bf, nstrips):
         assert np.array_equal(state, o.state), forcing
         # unconsumed draws stay queued: the generator is ahead of the oracle's by exactly len(pending)
     assert len(pending) < 37
+
+
+def test_negative_forcing_runs_to_the_end_like_the_reference():
+    """`reverted_particles < forcing` compares unsigned int with int in the reference (src/omp_lattice.cpp:264,346):
+    a negative forcing never stops on the count, only on the draw budget."""
+    from lgca_b200.capi import body_force_replay
+    cells = np.arange(50, dtype=np.int32)
+    state = np.full(50, 0x08, np.uint8)      # FHP: direction 3 set, direction 0 clear -> every draw reverts one particle
+    used, rev, ch_cells, ch_bytes = body_force_replay("FHP_III", "x", -1, cells, state)
+    assert (used, rev) == (50, 50)
+    assert np.array_equal(ch_bytes, np.full(50, 0x01, np.uint8))
+    used, rev, _, _ = body_force_replay("FHP_III", "x", 3, cells, state)
+    assert (used, rev) == (3, 3)

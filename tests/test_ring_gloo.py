@@ -73,6 +73,22 @@ class HostStripEngine:
         assert n <= self.halo
         self.o.step(n)
 
+    # body force stages of the strip interface (lgca_b200_body_force_gather / _apply)
+    def body_force_gather(self, cells):
+        s = self.o.state.reshape(self.rows, self.dim_x)
+        ct = self.o.cell_type.reshape(self.rows, self.dim_x)
+        gy, x = cells // self.dim_x, cells % self.dim_x
+        mine = (gy >= self.y0) & (gy < self.y0 + self.own)
+        r = np.where(mine, gy - self.y0 + self.halo, 0)
+        out = np.where(mine, s[r, x] | np.where(ct[r, x] != 0, 0x80, 0), 0x80).astype(np.uint8)
+        return out
+
+    def body_force_apply(self, cells, new_bytes):
+        s = self.o.state.reshape(self.rows, self.dim_x)
+        gy, x = cells // self.dim_x, cells % self.dim_x
+        mine = (gy >= self.y0) & (gy < self.y0 + self.own)
+        s[gy[mine] - self.y0 + self.halo, x[mine]] = new_bytes[mine]
+
     def own_state(self):
         return self.o.state.reshape(self.rows, self.dim_x)[self.halo: self.halo + self.own].ravel().copy()
 
@@ -124,3 +140,59 @@ def test_strips_match_single_lattice(world, model, dims, steps, halo):
     assert all(r[1] for r in res), res
     expect = -(-steps // halo)
     assert all(r[2] == expect for r in res)
+
+
+def _force_worker(rank, world, port, q):
+    """Exact body force on strips through lgca_b200.ring.ring_body_force (gather -> all-reduce MIN -> host replay ->
+    apply -> republish), then stepping on: the steps read the neighbours' ghost rows, so a missing republish shows."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
+    from cpu_checkers import Oracle, OracleRng
+    from lgca_b200.ring import Ring, ring_body_force
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    try:
+        model, dims, halo = "FHP_III", (64, 48), 2
+        o = Oracle(model, dims=dims, cg=1, bf_dir=b"x", rng=OracleRng(11))
+        o.apply_bc("pipe")
+        o.init("random")
+        y0, rows = partition_rows(dims[1], world, 2)[rank]
+        e = HostStripEngine(model, dims[0], dims[1], y0, rows, halo, o.state, o.cell_type, o.rnd)
+        ring = Ring(e, rank, world)
+
+        def combine(a):
+            t = torch.from_numpy(a.copy())
+            dist.all_reduce(t, op=dist.ReduceOp.MIN)
+            return t.numpy()
+
+        o.rng = OracleRng(31)
+        draws_rng, ok, pos = OracleRng(31), True, 0
+        stream = [draws_rng.rand() for _ in range(200000)]
+        for forcing in (0, 5, 300):
+            used_o, rev_o = o.body_force(forcing)
+            used, rev = ring_body_force(e, forcing, np.array(stream[pos:pos + used_o + 64], np.int64), o.num_cells, model, "x",
+                                        combine, ring=ring)
+            ok &= (used, rev) == (used_o, rev_o)
+            pos += used_o
+            ring.step(3)
+            o.step(3)
+            want = o.state.reshape(dims[1], dims[0])[y0: y0 + rows].ravel()
+            ok &= bool(np.array_equal(e.own_state(), want))
+        q.put((rank, ok))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_body_force_then_step_on_strips():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    world = 2
+    procs = [ctx.Process(target=_force_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    assert all(r[1] for r in res), res
