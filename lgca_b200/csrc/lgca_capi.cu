@@ -264,6 +264,7 @@ int lgca_b200_destroy(lgca_b200_lattice* h)
         cudaFree(h->snap);
     }
     for (int i = 0; i < 2; ++i) cudaFree(h->d_stage[i]);
+    cudaFree(h->res_exch); cudaFree(h->res_flags);
     cudaFree(h->snap_ghost); cudaFree(h->ns); cudaFree(h->sl); cudaFree(h->ch); cudaFree(h->xedge); cudaFree(h->d_flags);
     cudaFree(h->d_cell_density); cudaFree(h->d_cell_momentum); cudaFree(h->d_mean_density); cudaFree(h->d_mean_momentum);
     cudaFree(h->d_scalars); cudaFree(h->d_draws); cudaFree(h->d_draw_bytes);
@@ -406,6 +407,14 @@ static int step_impl(lgca_b200_lattice* h, int n_steps, bool check_halo)
                                            "generic kernel advances one step per exchange)", steps_per_launch(h, h->k_fuse), h->k_fuse);
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     const bool simple = (h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) != 0;
+    // lattices that fit on chip: ALL steps of the call in one launch of the SM-resident kernel
+    if (n_steps >= 2 && !simple && resident_supported(h)) {
+        int rc = launch_step_resident(h, h->planes[h->cur], h->planes[h->cur ^ 1], n_steps, h->s_compute);
+        if (rc) return rc;
+        h->cur ^= 1;
+        if (h->snap_spare) { h->planes[h->cur ^ 1] = h->snap_spare; h->snap_spare = nullptr; }
+        return 0;
+    }
     while (n_steps > 0) {
         int k = 1, rc;
         if (!simple) {

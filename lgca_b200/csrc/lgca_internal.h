@@ -94,6 +94,12 @@ struct lgca_b200_lattice {
     uint32_t         ring_inkernel_epoch;   // != 0: the next wave launch waits in-kernel for this epoch
     cudaStream_t     s_ring;                // pushes + signals run here, overlapped with the next step kernel
     cudaEvent_t      ev_step[2], ev_push[2];
+    // SM-resident kernel (lgca_step_resident.cu): ghost-row exchange area between CTAs and their progress counters
+    uint32_t*        res_exch;
+    uint32_t*        res_flags;
+    size_t           res_exch_words;
+    int              res_flags_n;
+    uint32_t         res_epoch;             // counters are monotonic across launches
 };
 
 namespace lgca_b200 {
@@ -112,6 +118,10 @@ int launch_step_simple(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, 
 // lgca_step_wave.cu : register wavefront, k steps per HBM pass
 int launch_step_wave(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
 bool wave_supported(const lgca_b200_lattice* h, int k);
+// lgca_step_resident.cu : the whole lattice in shared memory, n steps per launch (lattices of up to ~20 MB of planes)
+bool resident_supported(const lgca_b200_lattice* h);
+int launch_step_resident(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int n_steps, cudaStream_t s);
+int resident_info(const lgca_b200_lattice* h, int* ctas, int* steps_per_exchange, size_t* smem_bytes);
 int wave_prepare(lgca_b200_lattice* h);
 bool wave_has_edge_chunks(lgca_b200_lattice* h, int k);
 int simple_prepare(lgca_b200_lattice* h);
