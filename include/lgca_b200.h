@@ -56,8 +56,10 @@ enum {
 enum {
     LGCA_B200_FLAG_NO_CELL_FIELDS = 1u << 0, /* never produce per-cell float fields (>= 1e9-cell runs) */
     LGCA_B200_FLAG_SIMPLE_KERNEL  = 1u << 1, /* force the one-word-per-thread kernel (debug / A-B tests) */
-    LGCA_B200_FLAG_NO_RESIDENT    = 1u << 2  /* never use the SM-resident kernel (lattice kept in shared memory for all steps
+    LGCA_B200_FLAG_NO_RESIDENT    = 1u << 2, /* never use the SM-resident kernel (lattice kept in shared memory for all steps
                                                 of a call); A-B tests of the HBM-streaming wavefront kernel on small lattices */
+    LGCA_B200_FLAG_FORCE_RESIDENT = 1u << 3  /* use the SM-resident kernel whenever the lattice fits on chip, also where the
+                                                library's own choice would be the wavefront kernel (A-B tests) */
 };
 
 typedef struct lgca_b200_lattice lgca_b200_lattice; /* opaque */

@@ -12,6 +12,7 @@ NUM_DIR = {0: 4, 1: 6, 2: 7, 3: 7}
 FLAG_NO_CELL_FIELDS = 1 << 0
 FLAG_SIMPLE_KERNEL = 1 << 1
 FLAG_NO_RESIDENT = 1 << 2
+FLAG_FORCE_RESIDENT = 1 << 3
 
 # every symbol include/lgca_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [

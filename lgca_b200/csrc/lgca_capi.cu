@@ -264,7 +264,7 @@ int lgca_b200_destroy(lgca_b200_lattice* h)
         cudaFree(h->snap);
     }
     for (int i = 0; i < 2; ++i) cudaFree(h->d_stage[i]);
-    cudaFree(h->res_exch); cudaFree(h->res_flags);
+    cudaFree(h->res_exch);
     cudaFree(h->snap_ghost); cudaFree(h->ns); cudaFree(h->sl); cudaFree(h->ch); cudaFree(h->xedge); cudaFree(h->d_flags);
     cudaFree(h->d_cell_density); cudaFree(h->d_cell_momentum); cudaFree(h->d_mean_density); cudaFree(h->d_mean_momentum);
     cudaFree(h->d_scalars); cudaFree(h->d_draws); cudaFree(h->d_draw_bytes);

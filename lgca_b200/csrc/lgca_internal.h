@@ -95,11 +95,9 @@ struct lgca_b200_lattice {
     cudaStream_t     s_ring;                // pushes + signals run here, overlapped with the next step kernel
     cudaEvent_t      ev_step[2], ev_push[2];
     // SM-resident kernel (lgca_step_resident.cu): ghost-row exchange area between CTAs and their progress counters
-    uint32_t*        res_exch;
-    uint32_t*        res_flags;
+    uint32_t*        res_exch;              // {word, tag} messages
     size_t           res_exch_words;
-    int              res_flags_n;
-    uint32_t         res_epoch;             // counters are monotonic across launches
+    uint32_t         res_epoch;             // message tags are monotonic across launches
 };
 
 namespace lgca_b200 {

@@ -15,11 +15,13 @@
 //     for the 1-bit x-streaming come from shared memory too), runs the LOP3 collision / wall network of
 //     lgca_collide.cuh and stores into the other buffer; one __syncthreads per step.  Ghost rows are recomputed
 //     redundantly (trapezoid: after s steps the outermost s rows are stale), so K steps need no communication.
-//   * Every K steps the CTAs exchange ghost rows through L2: each CTA bulk-stores its top and bottom H rows into an
-//     exchange area (cp.async.bulk shared->global), publishes a counter with release semantics, and its two neighbours
-//     acquire it and bulk-load the rows into their ghost rows.  Only NEIGHBOURS synchronise -- no grid-wide barrier.
-//     The exchange area is double-buffered by block parity; the counter protocol orders every reuse (same argument as
-//     the multi-GPU ring, lgca_ring.cu).
+//   * Every K steps the CTAs exchange ghost rows through L2.  Only NEIGHBOURS synchronise -- no grid-wide barrier --
+//     and the message carries its own arrival flag: every 32-site word travels as one 8-byte store {word, tag}
+//     (single-copy atomic), tag = running block number, and the receiver polls the slot until the tag matches
+//     ("LL" protocol: one L2 write + one L2 read of latency, no fence, no separate flag; measured 5 us -> ~1 us per
+//     exchange against bulk store + release flag + acquire + bulk load).  The exchange area is double-buffered by block
+//     parity: a CTA overwrites block b's slots with block b+2's rows only after it consumed its neighbours' block b+1
+//     rows, which they sent after consuming block b (same argument as the multi-GPU ring, lgca_ring.cu).
 //   * Row ends: words are row-aligned here, so widths that are not a multiple of 32 only change where the carry bit
 //     of the x-shift comes from at the first / last word of a row.
 #include <string.h>
@@ -30,7 +32,10 @@
 
 namespace lgca_b200 {
 
-constexpr int RES_THREADS = 1024;
+#ifndef LGCA_RES_THREADS
+#define LGCA_RES_THREADS 768
+#endif
+constexpr int RES_THREADS = LGCA_RES_THREADS;   // four words per thread and step (85 registers each); measured 512 / 768 / 1024: 768 is best or close on every lattice
 constexpr int RES_MAX_SMEM = 227 * 1024; // opt-in dynamic shared memory per CTA on sm_100
 
 struct ResArgs {
@@ -40,9 +45,8 @@ struct ResArgs {
     const uint32_t* sl;
     const uint32_t* ch;
     const uint32_t* xedge;
-    uint32_t*       exch;     // [2 parities][G][2 sides][nd][H][pitch]
-    uint32_t*       flags;    // [G] blocks published by CTA j (monotonic over launches: + epoch_base)
-    uint32_t        epoch_base;
+    uint2*          exch;     // [2 parities][G][2 sides][nd][H][nw] of {word, tag}
+    uint32_t        epoch_base; // tags are monotonic over launches: tag of block b = epoch_base + b + 1
     uint32_t        rows, pitch, nw, rem, dim_y_south, dim_y_north; // rows of the lattice; stored rows of the N/S domain edges
     uint32_t        plane_stride;  // words between planes in global memory
     int             G;        // CTAs
@@ -95,15 +99,16 @@ __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wa
 // make generic-proxy writes (st.shared / ld.acquire results) visible to the async proxy (TMA) and vice versa
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
 
-__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p)
+// one 8-byte message {word, tag}: stored and loaded as a single access (single-copy atomic), straight to / from L2
+__device__ __forceinline__ void st_msg(uint2* p, uint32_t word, uint32_t tag)
 {
-    uint32_t v;
-    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+    asm volatile("st.relaxed.gpu.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(word), "r"(tag) : "memory");
 }
-__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v)
+__device__ __forceinline__ uint2 ld_msg(const uint2* p)
 {
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
 }
 
 // first row and height of CTA j's strip
@@ -112,6 +117,55 @@ __device__ __host__ __forceinline__ void res_strip(const ResArgs& A, int j, int&
     const int before = j * A.base_units + (j < A.extra_units ? j : A.extra_units);
     y0 = before * A.unit;
     R  = (A.base_units + (j < A.extra_units ? 1 : 0)) * A.unit;
+}
+
+// ---- four words (128 sites) of one row per thread -----------------------------------------------------------------
+// Everything is addressed in groups of four consecutive words: one LDS.128 / STS.128 per plane, the index arithmetic
+// is paid once per 128 sites.  Rows are `pitch` words long (a multiple of 4, padding words are zero); the last real
+// word of a row (index nw-1, possibly partial: rem = dim_x % 32 sites) may sit anywhere inside the last group.
+struct GroupCtx {
+    uint32_t left_off;  // word offset (inside the row) of the word left of the group: 4g-1, or nw-1 for the first group
+    uint32_t lsh;       // pre-shift that brings the last site of the row to bit 31 (first group of a partial row)
+    uint32_t right_off; // word offset of the word right of the group (unused in the last group)
+    bool     lastg;     // the group holds the last real word of the row
+    int      il;        // its position inside the group
+    uint32_t hi;        // bit of that word which receives site 0 in a down-shift (periodic wrap)
+};
+
+__device__ __forceinline__ uint4 lds4(const uint32_t* p) { return *reinterpret_cast<const uint4*>(p); }
+__device__ __forceinline__ void  sts4(uint32_t* p, uint4 v) { *reinterpret_cast<uint4*>(p) = v; }
+
+// site x <- site x-1 by `sh` (0 or 1) sites: row = plane row base (smem), g4 = 4*g
+__device__ __forceinline__ void shift_up4(uint32_t (&o)[4], const uint32_t* row, uint32_t g4, const GroupCtx& c, uint32_t sh)
+{
+    const uint4    v = lds4(row + g4);
+    const uint32_t L = row[c.left_off] << c.lsh;
+    o[0] = __funnelshift_l(L, v.x, sh);
+    o[1] = __funnelshift_l(v.x, v.y, sh);
+    o[2] = __funnelshift_l(v.y, v.z, sh);
+    o[3] = __funnelshift_l(v.z, v.w, sh);
+}
+// site x <- site x+1 by `sh` (0 or 1) sites
+__device__ __forceinline__ void shift_down4(uint32_t (&o)[4], const uint32_t* row, uint32_t g4, const GroupCtx& c, uint32_t sh)
+{
+    const uint4 v = lds4(row + g4);
+    uint32_t Rr = 0u;
+    if (!c.lastg) Rr = row[c.right_off];
+    o[0] = __funnelshift_r(v.x, v.y, sh);
+    o[1] = __funnelshift_r(v.y, v.z, sh);
+    o[2] = __funnelshift_r(v.z, v.w, sh);
+    o[3] = __funnelshift_r(v.w, Rr, sh);
+    if (c.lastg) {
+        // periodic wrap: the last real word takes site 0 of the row into its top site (the words after it are padding)
+        const uint32_t wrap = (row[0] & sh) << c.hi;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) o[i] |= (i == c.il) ? wrap : 0u;
+    }
+}
+__device__ __forceinline__ void plain4(uint32_t (&o)[4], const uint32_t* row, uint32_t g4)
+{
+    const uint4 v = lds4(row + g4);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
 }
 
 template <int MODEL, bool HAS_NS, bool HAS_SL>
@@ -123,7 +177,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) step_resident_kernel(const Res
     extern __shared__ __align__(128) uint32_t smem[];
     __shared__ __align__(8) uint64_t bar;
 
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int j   = blockIdx.x;
     int y0, R;
     res_strip(A, j, y0, R);
@@ -144,7 +198,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) step_resident_kernel(const Res
     }
     __syncthreads();
 
-    // ---- stage the strip + ghost rows (periodic in y) and the masks into shared memory --------------------------
+    // ---- stage the strip + ghost rows (periodic in y) and the masks into shared memory: TMA bulk copies ----------
     if (tid == 0) {
         const uint32_t row_bytes = (uint32_t)P * 4u;
         mbar_expect_tx(&bar, (uint32_t)(ND + NM) * (uint32_t)LR * row_bytes);
@@ -164,135 +218,127 @@ __global__ void __launch_bounds__(RES_THREADS, 1) step_resident_kernel(const Res
             gy = 0;
         }
     }
-    // rows are copied with their padding words (pitch > nw): keep them zero in the second buffer too (the first one got
-    // zeros from global memory), they travel to the exchange area and back to global memory with the rows
-    if (P > nw) {
-        const int pad = P - nw;
-        for (int e = tid; e < A.rows_max * pad * ND; e += RES_THREADS) {
-            const int d = e / (A.rows_max * pad), q = e % (A.rows_max * pad);
-            buf1[d * plane_sz + (q / pad) * P + nw + (q % pad)] = 0u;
-        }
-    }
+    // the second buffer starts out zero (padding words of rows that are never computed travel with the rows)
+    for (uint32_t e = tid; e < (uint32_t)ND * plane_sz / 4; e += RES_THREADS) sts4(buf1 + 4 * e, make_uint4(0u, 0u, 0u, 0u));
     mbar_wait(&bar, phase);
     phase ^= 1;
     __syncthreads();
 
-    // thread -> (row, word) stepping: element index e = tid, tid + T, ...; (dq, dr) = divmod(T, nw)
-    const int dq = RES_THREADS / nw, dr = RES_THREADS % nw;
-    const int q0 = tid / nw, w0 = tid % nw;
+    // thread -> (row, group) stepping: element index e = tid, tid + T, ...; (dq, dr) = divmod(T, groups per row)
+    const int PG = P / 4, gl = (nw - 1) / 4;                 // groups per row; group that holds the last real word
+    const int dq = RES_THREADS / PG, dr = RES_THREADS % PG;
+    const int q0 = tid / PG, g0 = tid % PG;
+    const uint32_t hi_last = rem ? (uint32_t)rem - 1u : 31u;
+    const uint32_t vm_last = rem ? ((1u << rem) - 1u) : 0xFFFFFFFFu;
 
     uint32_t* cur = buf0;
     uint32_t* nxt = buf1;
     const int n_blocks = (A.n_steps + A.K - 1) / A.K;
     const int lower = (j + A.G - 1) % A.G, upper = (j + 1) % A.G;
-    const size_t side_words = (size_t)ND * H * P;                  // one side of one CTA in the exchange area
-    const size_t parity_words = (size_t)A.G * 2 * side_words;
+    const int    side_n   = ND * H * nw;                            // messages of one side of one CTA
+    const size_t parity_n = (size_t)A.G * 2 * side_n;
+    constexpr int NWARPS = RES_THREADS / 32;
 
     for (int b = 0; b < n_blocks; ++b) {
         const int kb = min(A.K, A.n_steps - b * A.K);
         if (b > 0) {
-            // ghost rows of this block: the neighbours' edge rows after block b-1
-            if (tid == 0) {
-                const uint32_t want = A.epoch_base + (uint32_t)b;
-                while ((int32_t)(ld_acquire_gpu(A.flags + lower) - want) < 0) { }
-                while ((int32_t)(ld_acquire_gpu(A.flags + upper) - want) < 0) { }
-                fence_proxy_async();
-                const uint32_t* ex = A.exch + (size_t)((b - 1) & 1) * parity_words;
-                const uint32_t bytes = (uint32_t)H * P * 4u;
-                mbar_expect_tx(&bar, 2u * ND * bytes);
-#pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    // my lower ghost rows [0, H) <- the lower neighbour's TOP side; upper ghost rows <- upper neighbour's BOTTOM side
-                    bulk_g2s(cur + d * plane_sz, ex + ((size_t)lower * 2 + 1) * side_words + (size_t)d * H * P, bytes, &bar);
-                    bulk_g2s(cur + d * plane_sz + (size_t)(H + R) * P, ex + ((size_t)upper * 2 + 0) * side_words + (size_t)d * H * P, bytes, &bar);
+            // ghost rows of this block = the neighbours' edge rows after block b-1: poll every message until its tag
+            // shows.  One warp per (side, plane, row): consecutive lanes read consecutive 8-byte messages.
+            const uint32_t tag = A.epoch_base + (uint32_t)b;
+            const uint2* ex = A.exch + (size_t)((b - 1) & 1) * parity_n;
+            for (int rr = warp; rr < 2 * ND * H; rr += NWARPS) {
+                const int half = rr >= ND * H, i = half ? rr - ND * H : rr, d = i / H, row = i - d * H;
+                // lower ghost rows [0, H) <- the lower neighbour's TOP side; upper ghost rows <- the upper neighbour's BOTTOM side
+                const uint2* src = ex + ((size_t)(half ? upper : lower) * 2 + (half ? 0 : 1)) * side_n + (size_t)i * nw;
+                uint32_t* dst = cur + d * plane_sz + (size_t)((half ? H + R : 0) + row) * P;
+                for (int w = lane; w < nw; w += 32) {
+                    uint2 m;
+                    do { m = ld_msg(src + w); } while (m.y != tag);
+                    dst[w] = m.x;
                 }
             }
-            mbar_wait(&bar, phase);
-            phase ^= 1;
+            __syncthreads();
         }
         for (int s = 1; s <= kb; ++s) {
             // rows that are still needed and still valid after step s of this block
             const int ra = H - (kb - s), rb = H + R + (kb - s);
-            const int total = (rb - ra) * nw;
-            int r = ra + q0, w = w0;
+            const int total = (rb - ra) * PG;
+            int r = ra + q0, g = g0;
             for (int e = tid; e < total; e += RES_THREADS) {
-                const uint32_t rc = (uint32_t)r * P, rs = rc - P, rn = rc + P;
-                const bool first = (w == 0), last = (w == nw - 1);
-                const int  wl = first ? nw - 1 : w - 1, wr = last ? 0 : w + 1;
-                // carry bit of the 1-bit x-shifts at the row ends (periodic; the last word may be partial)
-                const int  lsh = (first && rem) ? 32 - rem : 0;      // pre-shift of the left neighbour word
-                const int  hi  = (last && rem) ? rem - 1 : 31;       // bit that receives site 0 in a down-shift
-#define S(d, ro, ww) cur[(d) * plane_sz + (ro) + (ww)]
-#define UP(d, ro)   __funnelshift_l(S(d, ro, wl) << lsh, S(d, ro, w), 1)
-#define DOWN(d, ro) ((S(d, ro, w) >> 1) | ((S(d, ro, wr) & 1u) << hi))
-                uint32_t n[7];
+                const uint32_t rc = (uint32_t)r * P, rs = rc - P, rn = rc + P, g4 = 4u * (uint32_t)g;
+                GroupCtx c;
+                c.lastg     = g >= gl;
+                c.il        = (nw - 1) - 4 * gl;
+                c.hi        = hi_last;
+                c.left_off  = g == 0 ? (uint32_t)nw - 1u : g4 - 1u;
+                c.lsh       = (g == 0 && rem) ? 32u - (uint32_t)rem : 0u;
+                c.right_off = g4 + 4u;
+                uint32_t in[7][4];
                 if (HPP) {
-                    n[0] = UP(0, rc);
-                    n[2] = DOWN(2, rc);
-                    n[1] = S(1, rs, w);
-                    n[3] = S(3, rn, w);
-                    n[4] = n[5] = n[6] = 0u;
+                    shift_up4(in[0], cur + 0 * plane_sz + rc, g4, c, 1u);
+                    shift_down4(in[2], cur + 2 * plane_sz + rc, g4, c, 1u);
+                    plain4(in[1], cur + 1 * plane_sz + rs, g4);
+                    plain4(in[3], cur + 3 * plane_sz + rn, g4);
                 } else {
-                    n[0] = UP(0, rc);
-                    n[3] = DOWN(3, rc);
-                    if (!(r & 1)) { // local parity == global parity (strip starts and H are even)
-                        n[1] = UP(1, rs);
-                        n[2] = S(2, rs, w);
-                        n[4] = S(4, rn, w);
-                        n[5] = UP(5, rn);
-                    } else {
-                        n[1] = S(1, rs, w);
-                        n[2] = DOWN(2, rs);
-                        n[4] = DOWN(4, rn);
-                        n[5] = S(5, rn, w);
-                    }
-                    n[6] = ND == 7 ? S(6, rc, w) : 0u;
+                    // odd/even hexagonal rows, branch-free: even rows shift planes 1 and 5 up, odd rows shift planes 2 and
+                    // 4 down; local parity == global parity (strip starts and H are even); a funnel shift by 0 passes through
+                    const uint32_t odd = (uint32_t)r & 1u, even = odd ^ 1u;
+                    shift_up4(in[0], cur + 0 * plane_sz + rc, g4, c, 1u);
+                    shift_down4(in[3], cur + 3 * plane_sz + rc, g4, c, 1u);
+                    shift_up4(in[1], cur + 1 * plane_sz + rs, g4, c, even);
+                    shift_down4(in[2], cur + 2 * plane_sz + rs, g4, c, odd);
+                    shift_down4(in[4], cur + 4 * plane_sz + rn, g4, c, odd);
+                    shift_up4(in[5], cur + 5 * plane_sz + rn, g4, c, even);
+                    if (ND == 7) plain4(in[6], cur + 6 * plane_sz + rc, g4);
                 }
-#undef S
-#undef UP
-#undef DOWN
-                const uint32_t p  = HPP ? 0u : m_ch[rc + w];
-                const uint32_t ns = HAS_NS ? m_ns[rc + w] : 0u;
-                const uint32_t sl = HAS_SL ? m_sl[rc + w] : 0u;
-                uint32_t ew = 0u, ns_row = 0u;
+                uint32_t pch[4] = {0u, 0u, 0u, 0u}, pns[4] = {0u, 0u, 0u, 0u}, psl[4] = {0u, 0u, 0u, 0u}, pew[4] = {0u, 0u, 0u, 0u};
+                if (!HPP) plain4(pch, m_ch + rc, g4);
+                if (HAS_NS) plain4(pns, m_ns + rc, g4);
+                uint32_t ns_row = 0u;
                 if (HAS_SL) {
-                    ew = __ldg(A.xedge + w);
+                    plain4(psl, m_sl + rc, g4);
+                    const uint4 ev = __ldg(reinterpret_cast<const uint4*>(A.xedge + g4));
+                    pew[0] = ev.x; pew[1] = ev.y; pew[2] = ev.z; pew[3] = ev.w;
                     int gy = y0 - H + r;                              // global (stored) row of this local row
                     if (gy < 0) gy += (int)A.rows; else if (gy >= (int)A.rows) gy -= (int)A.rows;
                     ns_row = ((uint32_t)gy == A.dim_y_south || (uint32_t)gy == A.dim_y_north) ? 0xFFFFFFFFu : 0u;
                 }
-                collide_and_walls<MODEL, HAS_NS, HAS_SL>(n, p, ns, sl, ew, ns_row);
-                const uint32_t vm = (last && rem) ? ((1u << rem) - 1u) : 0xFFFFFFFFu;
+                uint32_t out[7][4];
 #pragma unroll
-                for (int d = 0; d < ND; ++d) nxt[d * plane_sz + rc + w] = n[d] & vm;
-                r += dq; w += dr;
-                if (w >= nw) { w -= nw; ++r; }
+                for (int i = 0; i < 4; ++i) {
+                    uint32_t n[7];
+#pragma unroll
+                    for (int d = 0; d < 7; ++d) n[d] = d < ND ? in[d][i] : 0u;
+                    collide_and_walls<MODEL, HAS_NS, HAS_SL>(n, pch[i], pns[i], psl[i], pew[i], ns_row);
+                    // words after the last real word are padding (kept zero), the last real word may be partial
+                    const uint32_t vm = !c.lastg ? 0xFFFFFFFFu : (i < c.il ? 0xFFFFFFFFu : (i == c.il ? vm_last : 0u));
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) out[d][i] = n[d] & vm;
+                }
+#pragma unroll
+                for (int d = 0; d < ND; ++d) sts4(nxt + d * plane_sz + rc + g4, make_uint4(out[d][0], out[d][1], out[d][2], out[d][3]));
+                r += dq; g += dr;
+                if (g >= PG) { g -= PG; ++r; }
             }
             __syncthreads();
             uint32_t* t = cur; cur = nxt; nxt = t;
         }
         if (b + 1 < n_blocks) {
-            // publish my edge rows for the neighbours' next block
-            if (tid == 0) {
-                fence_proxy_async(); // the st.shared of the last step -> visible to the bulk stores
-                uint32_t* ex = A.exch + (size_t)(b & 1) * parity_words + (size_t)j * 2 * side_words;
-                const uint32_t bytes = (uint32_t)H * P * 4u;
-#pragma unroll
-                for (int d = 0; d < ND; ++d) {
-                    bulk_s2g(ex + (size_t)d * H * P, cur + d * plane_sz + (size_t)H * P, bytes);                 // BOTTOM side: rows [H, 2H)
-                    bulk_s2g(ex + side_words + (size_t)d * H * P, cur + d * plane_sz + (size_t)R * P, bytes);    // TOP side: rows [R, R+H)
-                }
-                bulk_commit();
-                bulk_wait_all();
-                fence_proxy_async();
-                st_release_gpu(A.flags + j, A.epoch_base + (uint32_t)b + 1u);
+            // publish my edge rows for the neighbours' next block (the last step ended with a __syncthreads)
+            const uint32_t tag = A.epoch_base + (uint32_t)b + 1u;
+            uint2* ex = A.exch + (size_t)(b & 1) * parity_n + (size_t)j * 2 * side_n;
+            for (int rr = warp; rr < 2 * ND * H; rr += NWARPS) {
+                const int side = rr >= ND * H, i = side ? rr - ND * H : rr, d = i / H, row = i - d * H;
+                // side 0 = BOTTOM: my lowest H owned rows [H, 2H); side 1 = TOP: my highest H owned rows [R, R+H)
+                const uint32_t* src = cur + d * plane_sz + (size_t)((side ? R : H) + row) * P;
+                uint2* dst = ex + (size_t)rr * nw;
+                for (int w = lane; w < nw; w += 32) st_msg(dst + w, src[w], tag);
             }
-            // (no block-wide sync needed here: the next block starts with the mbarrier wait led by thread 0)
         }
     }
-    // ---- write the strip back ------------------------------------------------------------------------------------
+    // ---- write the strip back: TMA bulk stores -------------------------------------------------------------------
     if (tid == 0) {
-        fence_proxy_async();
+        fence_proxy_async(); // the st.shared of the last step -> visible to the bulk stores
 #pragma unroll
         for (int d = 0; d < ND; ++d)
             bulk_s2g(A.out + (size_t)d * A.plane_stride + (size_t)y0 * P, cur + d * plane_sz + (size_t)H * P, (uint32_t)R * P * 4u);
@@ -315,6 +361,11 @@ static ResPlan res_plan(const lgca_b200_lattice* h)
     const Geom& g = h->g;
     if (g.halo != 0 || !g.wrap_y) return p;                       // whole lattices only
     if (h->cfg.flags & (LGCA_B200_FLAG_SIMPLE_KERNEL | LGCA_B200_FLAG_NO_RESIDENT)) return p;
+    // Where it pays (measured on B200, profiles/r02_small_lattices.md): every width that is not a multiple of 32 (the
+    // wavefront kernel's irregular-width variant is 2-3x slower than its regular one) and regular lattices below ~6 M
+    // sites, where the wavefront kernel cannot fill the machine.  Above that the wavefront kernel's K-step register
+    // blocking wins (HPP 4096^2, FHP-II 4096x2048).  LGCA_B200_FLAG_FORCE_RESIDENT overrides (A-B tests).
+    if (!(h->cfg.flags & LGCA_B200_FLAG_FORCE_RESIDENT) && g.rem == 0 && (uint64_t)g.dim_x * g.rows >= 6000000ull) return p;
     const bool hpp = rule_of(h->cfg.model) == MODEL_HPP;
     const int  nd = h->nd, nm = (hpp ? 0 : 1) + (h->has_ns ? 1 : 0) + (h->has_sl ? 1 : 0);
     const int  unit = hpp ? 1 : 2;
@@ -335,7 +386,7 @@ static ResPlan res_plan(const lgca_b200_lattice* h)
         p.ok = 1; p.G = G; p.unit = unit; p.base_units = base; p.extra_units = extra; p.H = H; p.K = K;
         p.rows_max = r_max + 2 * H;
         p.smem_bytes = smem;
-        p.exch_words = (size_t)2 * G * 2 * nd * H * g.pitch;
+        p.exch_words = (size_t)2 * G * 2 * nd * H * g.nw * 2; // {word, tag} messages
         return p;
     }
     return p;
@@ -368,22 +419,21 @@ int launch_step_resident(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out
     const ResPlan p = res_plan(h);
     if (!p.ok) return set_error(LGCA_B200_ESTATE, "lattice does not fit the SM-resident kernel");
     const Geom& g = h->g;
-    if (h->res_exch_words < p.exch_words || h->res_flags_n < p.G) {
-        // (re)allocation: nothing of this handle is in flight on the buffers after a stream sync
+    if (h->res_exch_words < p.exch_words) {
+        // (re)allocation: nothing of this handle is in flight on the buffer after a stream sync
         LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
-        cudaFree(h->res_exch); cudaFree(h->res_flags);
-        h->res_exch = nullptr; h->res_flags = nullptr; h->res_exch_words = 0; h->res_flags_n = 0;
+        if (h->res_exch) { cudaFree(h->res_exch); h->device_bytes -= h->res_exch_words * sizeof(uint32_t); }
+        h->res_exch = nullptr; h->res_exch_words = 0;
         LGCA_CUDA_CHECK(cudaMalloc((void**)&h->res_exch, p.exch_words * sizeof(uint32_t)));
-        LGCA_CUDA_CHECK(cudaMalloc((void**)&h->res_flags, (size_t)p.G * sizeof(uint32_t)));
-        LGCA_CUDA_CHECK(cudaMemset(h->res_flags, 0, (size_t)p.G * sizeof(uint32_t)));
+        LGCA_CUDA_CHECK(cudaMemset(h->res_exch, 0, p.exch_words * sizeof(uint32_t))); // tag 0 = "nothing here"
         LGCA_CUDA_CHECK(cudaDeviceSynchronize());
-        h->res_exch_words = p.exch_words; h->res_flags_n = p.G;
+        h->res_exch_words = p.exch_words;
         h->res_epoch = 0;
         h->device_bytes += p.exch_words * sizeof(uint32_t);
     }
     ResArgs A;
     A.in = in; A.out = out; A.ns = h->ns; A.sl = h->sl; A.ch = h->ch; A.xedge = h->xedge;
-    A.exch = h->res_exch; A.flags = h->res_flags; A.epoch_base = h->res_epoch;
+    A.exch = (uint2*)h->res_exch; A.epoch_base = h->res_epoch;
     A.rows = g.rows; A.pitch = g.pitch; A.nw = g.nw; A.rem = g.rem; A.dim_y_south = g.row_south; A.dim_y_north = g.row_north;
     A.plane_stride = (uint32_t)g.plane_stride;
     A.G = p.G; A.unit = p.unit; A.base_units = p.base_units; A.extra_units = p.extra_units; A.H = p.H; A.K = p.K;

@@ -3,7 +3,7 @@ device time per update for calls of 5 / 100 / 1000 steps (5 = one tick of the re
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lgca_b200
-from lgca_b200.capi import FLAG_NO_CELL_FIELDS, FLAG_NO_RESIDENT
+from lgca_b200.capi import FLAG_NO_CELL_FIELDS, FLAG_NO_RESIDENT, FLAG_FORCE_RESIDENT
 
 CONFIGS = [
     ("C1 lgca-pipe FHP-I 1400x700", "FHP_I", 1400, 700, "pipe"),
@@ -12,12 +12,18 @@ CONFIGS = [
     ("C2 lgca-diffusion HPP 4096x4096", "HPP", 4096, 4096, "periodic"),
     ("HPP 4096x4096 bounce-back frame", "HPP", 4096, 4096, "reflecting_back"),
     ("FHP-III 2048x2048 periodic", "FHP_III", 2048, 2048, "periodic"),
+    ("HPP 2048x2048 periodic", "HPP", 2048, 2048, "periodic"),
+    ("HPP 1024x1024 periodic", "HPP", 1024, 1024, "periodic"),
+    ("FHP-II 4096x2048 box", "FHP_II", 4096, 2048, "reflecting_back"),
+    ("FHP-III 256x256 periodic (app 'periodic' default)", "FHP_III", 256, 256, "periodic"),
 ]
+if os.environ.get("SMALL_ONLY_RESIDENT"):
+    pass
 KS = [int(a) for a in sys.argv[1:]] or [0]
 print("| lattice | kernel | k | us/update @5 | us/update @100 | us/update @1000 | site updates/s @1000 |")
 print("|---|---|---:|---:|---:|---:|---:|")
 for name, model, dx, dy, bc in CONFIGS:
-    for kernel, flags in (("wave", FLAG_NO_RESIDENT), ("resident", 0)):
+    for kernel, flags in ((("resident", FLAG_FORCE_RESIDENT),) if os.environ.get("SMALL_ONLY_RESIDENT") else (("wave", FLAG_NO_RESIDENT), ("resident", FLAG_FORCE_RESIDENT))):
         for k in (KS if kernel == "resident" else [0]):
             e = lgca_b200.Engine(model, dx, dy, k_fuse=k, flags=flags | FLAG_NO_CELL_FIELDS)
             e.apply_bc_device(bc)

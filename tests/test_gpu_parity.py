@@ -28,14 +28,14 @@ def engine_from(o, k_fuse=0, flags=0, **kw):
 
 # flags: 2 = generic one-word-per-thread kernel; 4 = never use the SM-resident kernel, i.e. the HBM-streaming wavefront
 # kernel with k fused steps; 0 = library default: lattices that fit on chip run the SM-resident kernel (k = steps per
-# ghost-row exchange between CTAs) whenever a call advances >= 2 steps
+# ghost-row exchange between CTAs) whenever a call advances >= 2 steps; 8 = force it wherever the lattice fits
 VARIANTS = [pytest.param(dict(flags=2), id="simple"), pytest.param(dict(k_fuse=1, flags=4), id="k1"),
             pytest.param(dict(k_fuse=2, flags=4), id="k2"), pytest.param(dict(k_fuse=3, flags=4), id="k3"),
             pytest.param(dict(k_fuse=4, flags=4), id="k4"), pytest.param(dict(k_fuse=6, flags=4), id="k6"),
             pytest.param(dict(flags=4), id="default"),
-            pytest.param(dict(k_fuse=1), id="res1"), pytest.param(dict(k_fuse=2), id="res2"),
-            pytest.param(dict(k_fuse=3), id="res3"), pytest.param(dict(k_fuse=5), id="res5"),
-            pytest.param(dict(), id="res")]
+            pytest.param(dict(k_fuse=1, flags=8), id="res1"), pytest.param(dict(k_fuse=2, flags=8), id="res2"),
+            pytest.param(dict(k_fuse=3, flags=8), id="res3"), pytest.param(dict(k_fuse=5, flags=8), id="res5"),
+            pytest.param(dict(flags=8), id="res"), pytest.param(dict(), id="auto")]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
@@ -292,7 +292,7 @@ def test_extreme_occupancies(model, fill):
     # solid cells may hold particles too (they stream in and bounce): exercise that as well
     if fill == "dense":
         o.state[~fluid] = rs.randint(0, 1 << nd, size=int((~fluid).sum())).astype(np.uint8)
-    for variant in (dict(flags=2), dict(k_fuse=3, flags=4), dict(flags=4), dict(k_fuse=3), dict()):
+    for variant in (dict(flags=2), dict(k_fuse=3, flags=4), dict(flags=4), dict(k_fuse=3, flags=8), dict()):
         e = engine_from(o, **variant)
         oo = Oracle(model, dims=(200, 66), cg=1)
         oo.state[:], oo.cell_type[:], oo.rnd[:] = o.state, o.cell_type, o.rnd
