@@ -546,6 +546,9 @@ def run_b200_arm(args):
             teardown(e, world)
             line["karman"] = karman_extra(args, peak)
             line["diffusion_hpp"] = hpp_extra(args, peak)
+            line["resident"] = resident_extra(args)
+            if not args.no_app_tick:
+                line["app_tick"] = app_tick_extra()
     if args.workload == "periodic" and not args.no_box:
         # C4 at this N (all ranks take part); the main engine goes first: 65536 x 32768 needs the memory
         teardown(e, world)
@@ -627,6 +630,93 @@ def box_extra(args, rank, world, local_rank, device, peak):
             "particles_conserved": bool(n0 == n1)}
 
 
+def app_tick_extra():
+    """The reference's REAL app schedule end to end (apps/karman/karman_viewer.cpp:100-184: mean velocity -> body force ->
+    5 steps -> snapshot -> post-process per tick), 1000 steps: the headless C++ apps on B200_Lattice (host rand() stream,
+    order-exact host mean velocity, exact body force -- the bit-exact path the parity tests check) against the same
+    schedule on the unmodified reference (oracle/_ref) on the host cores (bounded number of ticks)."""
+    import re
+    out = {}
+    bin_dir = os.path.join(ROOT, "lgca_b200", "host", "bin")
+    cases = [("pipe_c1", "lgca-pipe", ["--model", "FHP_I"], ("FHP_I", "pipe", 80.0, 0.3, 10, "pipe"), 40),
+             ("karman_default", "lgca-karman", [], ("FHP_III", "karman", 80.0, 0.3, 20, "karman"), 8)]
+    for key, app, extra, ref_cfg, ref_ticks in cases:
+        ent = {}
+        exe = os.path.join(bin_dir, app)
+        if os.path.exists(exe):
+            p = subprocess.run([exe, "--steps", "1000", "--quiet"] + extra, capture_output=True, text=True)
+            m = re.search(r"Tick loop: (\S+) s wall for (\d+) steps in (\d+) ticks \(mean velocity (\S+) s, body force (\S+) s, "
+                          r"stepping (\S+) s, snapshot \+ post-process (\S+) s\); (\S+) site updates/s", p.stdout)
+            if m and p.returncode == 0:
+                ent["b200"] = {"steps": int(m.group(2)), "ticks": int(m.group(3)), "wall_s": float(m.group(1)),
+                               "mean_velocity_s": float(m.group(4)), "body_force_s": float(m.group(5)), "stepping_s": float(m.group(6)),
+                               "post_process_s": float(m.group(7)), "site_updates_per_s": float(m.group(8)),
+                               "ms_per_tick": float(m.group(1)) / int(m.group(3)) * 1e3}
+            else:
+                ent["b200"] = {"error": (p.stdout + p.stderr)[-300:]}
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            import cpu_checkers as cc
+            if cc.ref_available():
+                model, case, Re, Ma, cg, bc = ref_cfg
+                cores = os.cpu_count() or 1
+                r = cc.Ref(model, case, Re, Ma, cg, threads=1)
+                r.apply_bc(bc)
+                r.init("random")
+                r.set_threads(cores)
+                r.snapshot(); r.post_process()
+                forcing, u = r.initial_forcing(), r.u
+                t0 = time.perf_counter()
+                for _ in range(ref_ticks):
+                    r.set_threads(1)       # the reference's racy counter needs one thread to be deterministic
+                    mv = r.mean_velocity()
+                    r.set_threads(cores)
+                    if mv[0] < u:
+                        if mv[0] > 0.9 * u:
+                            forcing = r.equilibrium_forcing()
+                        r.body_force(forcing)
+                    r.step(5)
+                    r.snapshot(); r.post_process()
+                dt = time.perf_counter() - t0
+                ent["reference"] = {"ticks": ref_ticks, "steps": 5 * ref_ticks, "wall_s": dt, "ms_per_tick": dt / ref_ticks * 1e3,
+                                    "site_updates_per_s": r.num_cells * 5 * ref_ticks / dt, "cores": cores}
+                r.close()
+        except Exception as ex:
+            ent["reference"] = {"error": repr(ex)}
+        if "b200" in ent and "reference" in ent and "ms_per_tick" in ent["b200"] and "ms_per_tick" in ent["reference"]:
+            ent["tick_speedup"] = ent["reference"]["ms_per_tick"] / ent["b200"]["ms_per_tick"]
+        out[key] = ent
+    return out
+
+
+def resident_extra(args):
+    """Lattices that fit on chip (the reference's own app sizes): device time per update of the SM-resident kernel
+    (library default there) against the HBM-streaming wavefront kernel, for one viewer tick (5 steps) and a long call."""
+    import lgca_b200
+    from lgca_b200.capi import FLAG_NO_CELL_FIELDS, FLAG_NO_RESIDENT
+    out = {}
+    dev = int(os.environ.get("LOCAL_RANK", "0"))
+    for key, model, dx, dy, bc in (("pipe_c1_fhp1_1400x700", "FHP_I", 1400, 700, "pipe"), ("pipe_default_fhp3_1480x740", "FHP_III", 1480, 740, "pipe"),
+                                   ("karman_default_fhp3_4400x2200", "FHP_III", 4400, 2200, "karman"),
+                                   ("hpp_2048x2048", "HPP", 2048, 2048, "periodic")):
+        ent = {}
+        for kernel, flags in (("resident", 0), ("wave", FLAG_NO_RESIDENT)):
+            e = lgca_b200.Engine(model, dx, dy, device=dev, flags=flags | FLAG_NO_CELL_FIELDS)
+            e.apply_bc_device(bc)
+            e.init_random_device(1)
+            res = {}
+            for n, reps in ((5, 100), (1000, 3)):
+                e.timed_steps(n)
+                best = min(sum(e.timed_steps(n) for _ in range(reps)) / reps for _ in range(3))
+                res["us_per_update_call_of_%d" % n] = best * 1e3 / n
+            res["site_updates_per_s"] = dx * dy / (res["us_per_update_call_of_1000"] * 1e-6)
+            ent[kernel] = res
+            e.close()
+        ent["speedup"] = ent["wave"]["us_per_update_call_of_1000"] / ent["resident"]["us_per_update_call_of_1000"]
+        out[key] = ent
+    return out
+
+
 def karman_extra(args, peak):
     """Config C3 on one GPU: device-resident throughput and kernel roofline (attached to the default line)."""
     e = build_engine("karman", 0, 1, int(os.environ.get("LOCAL_RANK", "0")), args.k_fuse)
@@ -677,6 +767,7 @@ def main():
     ap.add_argument("--no-vti", action="store_true", help="skip the .vti write of the coarse fields")
     ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU decomposition-invariance check (N > 1)")
     ap.add_argument("--no-box", action="store_true", help="skip the C4 box extra")
+    ap.add_argument("--no-app-tick", action="store_true", help="skip the end-to-end app schedule extra")
     ap.add_argument("--nccl-halo", action="store_true", help="move ghost rows with NCCL send/recv instead of the native peer-store ring")
     args = ap.parse_args()
     if args.impl == "reference":

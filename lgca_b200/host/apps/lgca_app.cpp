@@ -15,6 +15,7 @@
 #include <string>
 
 #include "../b200_lattice.h"
+#include "../lgca_io_png.h"
 #include "../lgca_io_vti.h"
 
 #ifndef LGCA_APP_CASE
@@ -34,7 +35,8 @@ struct Args {
     int         hash_every = 0;
     unsigned    dim_x = 0, dim_y = 0;
     bool        cell_fields = true, quiet = false, bc_forward = false;
-    std::string output = "none", out_dir = "./";
+    std::string output = "none", out_dir = "./", scalars = "Mean momentum";
+    int         zoom = 1;
 };
 
 uint64_t fnv1a64(const uint8_t* p, size_t n)
@@ -48,7 +50,7 @@ void usage(const char* argv0)
 {
     printf("usage: %s [-r Re] [-m Ma] [-d 4|6|7] [--model HPP|FHP_I|FHP_II|FHP_III] [-s steps] [-c cg-radius]\n"
            "          [-w write-steps] [--pp-interval n] [--dims X Y] [--device n] [--gpus n | --devices a,b,..] [--k-fuse k]\n"
-           "          [-o none|vti|png] [--out-dir d]\n"
+           "          [-o none|vti|png] [--out-dir d] [--scalars \"Mean momentum\"] [--zoom n]\n"
            "          [--hash-every n] [--bounce forward|back] [--no-cell-fields] [--quiet]\n", argv0);
 }
 
@@ -91,6 +93,8 @@ bool parse(int argc, char** argv, Args& a)
         else if (f == "--k-fuse") a.k_fuse = atoi(next("k-fuse"));
         else if (f == "-o" || f == "--output") a.output = next("output");
         else if (f == "--out-dir") a.out_dir = next("out-dir");
+        else if (f == "--scalars") a.scalars = next("scalars");   // "Cell density" | "Cell momentum" | "Mean density" | "Mean momentum"
+        else if (f == "--zoom") a.zoom = atoi(next("zoom"));
         else if (f == "--hash-every") a.hash_every = atoi(next("hash-every"));
         else if (f == "--bounce") a.bc_forward = std::string(next("bounce")) == "forward";
         else if (f == "--no-cell-fields") a.cell_fields = false;
@@ -142,6 +146,7 @@ int run(const Args& a)
     int forcing = (int)lat->get_initial_forcing();
     lat->setup_parallel();
     IoVti<M> vti(lat);
+    IoPng<M> png(lat, a.scalars, (unsigned)a.zoom);
     const bool forced = (tc == "pipe" || tc == "karman");
 
     auto print_hash = [&](size_t step) {
@@ -150,37 +155,54 @@ int run(const Args& a)
     };
     if (a.hash_every) print_hash(0);
 
-    size_t steps = 0;
-    double sim_seconds = 0;
+    size_t steps = 0, ticks = 0;
+    double sim_seconds = 0, t_mv = 0, t_bf = 0, t_pp = 0;
     std::vector<Real> mv(2, 0.0);
+    using clk = std::chrono::steady_clock;
+    auto secs = [](clk::time_point a, clk::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+    const auto loop_start = clk::now();
     while ((int)steps < a.steps) {
         if (forced) {
+            auto t0 = clk::now();
             mv = lat->get_mean_velocity();
+            auto t1 = clk::now();
             if (mv[0] < lat->u()) {
                 if (mv[0] > 0.9 * lat->u()) forcing = (int)lat->get_equilibrium_forcing();
                 lat->apply_body_force(forcing);
             }
+            lat->synchronize();
+            t_mv += secs(t0, t1);
+            t_bf += secs(t1, clk::now());
         }
         const int n = std::min(a.pp_interval, a.steps - (int)steps);
         lat->synchronize();
-        auto t0 = std::chrono::steady_clock::now();
+        auto t0 = clk::now();
         lat->collide_and_propagate_n(n);
         lat->synchronize();
-        sim_seconds += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        auto t1 = clk::now();
+        sim_seconds += secs(t0, t1);
         steps += n;
+        ++ticks;
         lat->copy_data_to_output_buffer();
         lat->post_process();
+        t_pp += secs(t1, clk::now());
         if (a.write_steps > 0 && steps % a.write_steps == 0) {
             if (!a.quiet) printf("Executing step %zu... mean velocity (%6.4f, %6.4f)\n", steps, mv[0], mv[1]);
             if (a.output == "vti") vti.write(steps, a.out_dir);
+            else if (a.output == "png") png.write(steps, a.out_dir);
         }
         if (a.hash_every && steps % a.hash_every == 0) print_hash(steps);
     }
+    const double loop_seconds = secs(loop_start, clk::now());
     const unsigned long particles_end = lat->get_n_particles();
     if (particles_end == particles_start) printf("Error check PASSED: There is no difference in the number of particles.\n");
     else printf("Error check FAILED: There is a difference in the number of particles of %ld.\n", (long)particles_end - (long)particles_start);
     printf("Total simulation time: %e s for %zu simulation steps.\n", sim_seconds, steps);
     if (sim_seconds > 0) printf("Average MNUPS: %.0f\n", (double)lat->num_cells() * steps / (sim_seconds * 1.0e06));
+    // the whole tick loop as the viewers run it: mean velocity -> body force -> steps -> snapshot + post-process
+    printf("Tick loop: %e s wall for %zu steps in %zu ticks (mean velocity %e s, body force %e s, stepping %e s, "
+           "snapshot + post-process %e s); %.0f site updates/s end to end.\n", loop_seconds, steps, ticks, t_mv, t_bf, sim_seconds,
+           t_pp, loop_seconds > 0 ? (double)lat->num_cells() * steps / loop_seconds : 0.0);
     if (forced) printf("Mean velocity: %.9g %.9g\n", mv[0], mv[1]);
     print_hash(steps);
     delete lat;

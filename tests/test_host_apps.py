@@ -163,3 +163,23 @@ def test_vti_output_matches_oracle(apps, tmp_path):
     assert ext == (7, 7)
     assert np.array_equal(mean["Mean density"], o.mean_density)
     assert np.array_equal(mean["Mean momentum"], o.mean_momentum)
+
+
+@pytest.mark.gpu
+def test_png_output_matches_oracle_field(apps, tmp_path):
+    """-o png (the viewers' OUTPUT_FORMAT, apps/karman/karman_viewer.h:87): res_<step>.png shows |mean momentum| of the
+    snapshot over its own range through the blue->red table; compared per coarse cell with the oracle's field."""
+    from cpu_checkers import Oracle
+    from test_png_writer import read_png, vtk_rainbow
+    out = str(tmp_path) + "/"
+    run_app("lgca-periodic", "-r", 255, "-c", 16, "--steps", 20, "--pp-interval", 10, "-w", 20, "-o", "png", "--out-dir", out, "--quiet")
+    o = Oracle("FHP_III", "periodic", 255.0, 0.2, 16)
+    o.apply_bc("periodic")
+    o.init("random")
+    o.step(20)
+    o.snapshot()
+    o.post_process()
+    img = read_png(out + "res_20.png")
+    m = o.mean_momentum.reshape(8, 8, 2)
+    mag = np.sqrt(m[..., 0] * m[..., 0] + m[..., 1] * m[..., 1]).astype(np.float32)
+    assert np.array_equal(img, vtk_rainbow(mag, float(mag.min()), float(mag.max()))[::-1])
