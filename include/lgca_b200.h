@@ -58,8 +58,10 @@ enum {
     LGCA_B200_FLAG_SIMPLE_KERNEL  = 1u << 1, /* force the one-word-per-thread kernel (debug / A-B tests) */
     LGCA_B200_FLAG_NO_RESIDENT    = 1u << 2, /* never use the SM-resident kernel (lattice kept in shared memory for all steps
                                                 of a call); A-B tests of the HBM-streaming wavefront kernel on small lattices */
-    LGCA_B200_FLAG_FORCE_RESIDENT = 1u << 3  /* use the SM-resident kernel whenever the lattice fits on chip, also where the
+    LGCA_B200_FLAG_FORCE_RESIDENT = 1u << 3, /* use the SM-resident kernel whenever the lattice fits on chip, also where the
                                                 library's own choice would be the wavefront kernel (A-B tests) */
+    LGCA_B200_FLAG_HOST_BODY_FORCE = 1u << 4 /* lgca_b200_body_force through gather -> host replay -> apply instead of the
+                                                device-side prefix (A-B tests; row strips always take this route) */
 };
 
 typedef struct lgca_b200_lattice lgca_b200_lattice; /* opaque */
@@ -124,13 +126,31 @@ int  lgca_b200_post_process(lgca_b200_lattice* h, float* cell_density, float* ce
  * Device reduction over the snapshot (double accumulation; NOT the reference's sequential float32
  * order -- the order-exact variant runs in B200_Lattice on the host fields, as the reference does). */
 int  lgca_b200_mean_velocity(lgca_b200_lattice* h, float out[2]);
+/* Order-exact variant: CONTINUES the reference's sequential float32 sums (sum_x_vel, sum_y_vel and the FLUID-cell
+ * counter of src/omp_lattice.cpp:513-549, as they come out at ONE thread) over this handle's rows of the SNAPSHOT, in
+ * cell order, from the running values in sums[] / *fluid_cells.  Start them at 0, call the strips of a lattice in y
+ * order and divide at the end: mean_velocity[i] = sums[i] / (float)fluid_cells (:553-554).  The device reduces every
+ * 1024-cell segment to integer summaries per float32 binade, the host walks the segments (see csrc/lgca_mv.cu);
+ * bit-equal to the reference loop.  Synchronous; post-processing stream.  At most 2^28 cells per handle. */
+int  lgca_b200_mean_velocity_exact(lgca_b200_lattice* h, float sums[2], uint64_t* fluid_cells);
+/* diagnostic counters of the calls so far: segments taken as one integer add, segments walked cell by cell,
+ * nanoseconds spent on the device + copies, nanoseconds spent in the host walk */
+int  lgca_b200_mean_velocity_stats(lgca_b200_lattice* h, uint64_t out[4]);
+/* Host-only (no GPU) restatement of the same algorithm on a row-major array of class bytes (state byte of a FLUID
+ * cell, 0 for solid cells), with the segment summaries computed on the CPU: the checker of the walk logic in the CPU
+ * test-suite.  segments_fast / segments_walked (optional) count how the segments were taken. */
+int  lgca_b200_mean_velocity_replay(int model, const uint8_t* class_bytes, uint32_t dim_x, uint32_t rows, float sums[2],
+                                    uint64_t* segments_fast, uint64_t* segments_walked);
 
 /* ---- Lattice::apply_body_force(), src/lattice.h:200 / src/omp_lattice.cpp:254-346 ----
  * Exact, draw-order-preserving body force.  `draws` are the caller's `rand()` values in stream order
  * (each is reduced `% num_cells` like src/omp_lattice.cpp:269).  Draws are consumed in order until
  * `forcing` particles have been reverted or `n_draws` are used up; *consumed and *reverted report the
  * progress so the caller can continue with more draws (the reference stops after 2*num_cells draws;
- * that cap is the caller's, see B200_Lattice::apply_body_force).  Operates on the live state. */
+ * that cap is the caller's, see B200_Lattice::apply_body_force).  Operates on the live state.
+ * Whole-lattice handles run the batch entirely on the device (csrc/lgca_bodyforce.cu: first occurrence of every
+ * drawn cell through a hash table, gains from the bit-planes, prefix sum, the do-while's stop rule, scatter); the
+ * only host synchronisation is the read-back of *consumed / *reverted. */
 int  lgca_b200_body_force(lgca_b200_lattice* h, int forcing, const int32_t* draws, size_t n_draws,
                           size_t* consumed, uint32_t* reverted);
 
@@ -245,6 +265,8 @@ int  lgca_b200_group_snapshot(lgca_b200_group* g);
 int  lgca_b200_group_post_process(lgca_b200_group* g, float* cell_density, float* cell_momentum, float* mean_density,
                                   float* mean_momentum, int exact_order);
 int  lgca_b200_group_mean_velocity(lgca_b200_group* g, float out[2]);
+/* order-exact (lgca_b200_mean_velocity_exact chained over the strips in y order, then the final divisions) */
+int  lgca_b200_group_mean_velocity_exact(lgca_b200_group* g, float out[2]);
 int  lgca_b200_group_body_force(lgca_b200_group* g, int forcing, const int32_t* draws, size_t n_draws, size_t* consumed,
                                 uint32_t* reverted);
 int  lgca_b200_group_count_particles(lgca_b200_group* g, uint64_t* out);

@@ -110,16 +110,12 @@ public:
     // sequential float32 sums over the per-cell host fields of the last post_process(), one thread: the only order that
     // reproduces the digits of src/omp_lattice.cpp:508-557
     std::vector<Real> get_mean_velocity() {
+        // order-exact on the device (the one-thread float32 sums of src/omp_lattice.cpp:508-557, see csrc/lgca_mv.cu)
         std::vector<Real> v(this->SPATIAL_DIM, 0.0);
-        Real sx = 0.0, sy = 0.0;
-        size_t fluid = 0;
-        for (size_t n = 0; n < this->m_num_cells; ++n) {
-            if (this->m_cell_type_cpu[n] != CellType::FLUID) continue;
-            ++fluid;
-            const Real rho = this->m_cell_density_cpu[n];
-            if (rho > 1.0e-06) { sx += this->m_cell_momentum_cpu[2 * n] / rho; sy += this->m_cell_momentum_cpu[2 * n + 1] / rho; }
-        }
-        v[0] = sx / (Real)fluid; v[1] = sy / (Real)fluid;
+        ensure_on_device();
+        float out[2];
+        check(lgca_b200_group_mean_velocity_exact(m_h, out), "get_mean_velocity");
+        v[0] = out[0]; v[1] = out[1];
         return v;
     }
     // rand() values are drawn ahead into a FIFO, consumed in order by the exact device body force, leftovers are kept:

@@ -19,7 +19,8 @@ SYMBOLS = [
     "lgca_b200_create", "lgca_b200_destroy", "lgca_b200_last_error", "lgca_b200_version",
     "lgca_b200_device_count", "lgca_b200_host_alloc", "lgca_b200_host_free", "lgca_b200_upload",
     "lgca_b200_download", "lgca_b200_step", "lgca_b200_snapshot", "lgca_b200_post_process",
-    "lgca_b200_mean_velocity", "lgca_b200_body_force", "lgca_b200_body_force_gather", "lgca_b200_body_force_replay",
+    "lgca_b200_mean_velocity", "lgca_b200_mean_velocity_exact", "lgca_b200_mean_velocity_replay", "lgca_b200_mean_velocity_stats",
+    "lgca_b200_group_mean_velocity_exact", "lgca_b200_body_force", "lgca_b200_body_force_gather", "lgca_b200_body_force_replay",
     "lgca_b200_body_force_apply", "lgca_b200_count_particles",
     "lgca_b200_init_random_device", "lgca_b200_apply_bc_device", "lgca_b200_sync",
     "lgca_b200_compute_stream", "lgca_b200_timed_steps", "lgca_b200_timed_kernel", "lgca_b200_launch_count", "lgca_b200_get_info",
@@ -82,6 +83,10 @@ def load_library():
     L.lgca_b200_snapshot.argtypes = [vp]
     L.lgca_b200_post_process.argtypes = [vp, vp, vp, vp, vp, i32]
     L.lgca_b200_mean_velocity.argtypes = [vp, vp]
+    L.lgca_b200_mean_velocity_exact.argtypes = [vp, vp, C.POINTER(u64)]
+    L.lgca_b200_mean_velocity_replay.argtypes = [i32, vp, C.c_uint32, C.c_uint32, vp, C.POINTER(u64), C.POINTER(u64)]
+    L.lgca_b200_group_mean_velocity_exact.argtypes = [vp, vp]
+    L.lgca_b200_mean_velocity_stats.argtypes = [vp, vp]
     L.lgca_b200_body_force.argtypes = [vp, i32, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32)]
     L.lgca_b200_body_force_gather.argtypes = [vp, vp, C.c_size_t, vp]
     L.lgca_b200_body_force_replay.argtypes = [i32, i32, i32, vp, vp, C.c_size_t, C.POINTER(C.c_size_t), C.POINTER(C.c_uint32),
@@ -135,6 +140,21 @@ def load_library():
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def mean_velocity_replay(model, class_bytes, dim_x, rows, sums=(0.0, 0.0)):
+    """Host-only order-exact mean-velocity sums over a row-major array of class bytes (lgca_b200_mean_velocity_replay).
+    Returns (sums float32[2], segments_fast, segments_walked)."""
+    L = load_library()
+    model = MODELS[model] if isinstance(model, str) else int(model)
+    cls = np.ascontiguousarray(class_bytes, np.uint8)
+    assert cls.size == dim_x * rows
+    out = np.array(sums, np.float32)
+    fast, walked = C.c_uint64(0), C.c_uint64(0)
+    rc = L.lgca_b200_mean_velocity_replay(model, _ptr(cls), int(dim_x), int(rows), _ptr(out), C.byref(fast), C.byref(walked))
+    if rc != 0:
+        raise LgcaError(L.lgca_b200_last_error().decode())
+    return out, int(fast.value), int(walked.value)
 
 
 def body_force_replay(model, bf_dir, forcing, cells, cell_bytes):
@@ -264,6 +284,19 @@ class Engine:
                                                   _ptr(out.get("mean_density")), _ptr(out.get("mean_momentum")),
                                                   1 if exact else 0))
         return out
+
+    def mean_velocity_exact(self, sums=(0.0, 0.0), fluid_cells=0):
+        """Continues the reference's sequential float32 sums over this handle's rows; returns (sums, fluid_cells)."""
+        out = np.array(sums, np.float32)
+        cnt = C.c_uint64(int(fluid_cells))
+        self._check(self.L.lgca_b200_mean_velocity_exact(self.h, _ptr(out), C.byref(cnt)))
+        return out, int(cnt.value)
+
+    def mean_velocity_stats(self):
+        """{segments_fast, segments_walked, device_ns, walk_ns} accumulated over the mean_velocity_exact calls so far."""
+        out = np.zeros(4, np.uint64)
+        self._check(self.L.lgca_b200_mean_velocity_stats(self.h, _ptr(out)))
+        return dict(zip(("segments_fast", "segments_walked", "device_ns", "walk_ns"), (int(v) for v in out)))
 
     def mean_velocity(self):
         out = np.zeros(2, np.float32)
@@ -449,6 +482,11 @@ class Group:
         self._check(self.L.lgca_b200_group_post_process(self.g, _ptr(out.get("cell_density")), _ptr(out.get("cell_momentum")),
                                                         _ptr(out.get("mean_density")), _ptr(out.get("mean_momentum")),
                                                         1 if exact else 0))
+        return out
+
+    def mean_velocity_exact(self):
+        out = np.zeros(2, np.float32)
+        self._check(self.L.lgca_b200_group_mean_velocity_exact(self.g, _ptr(out)))
         return out
 
     def mean_velocity(self):

@@ -265,6 +265,8 @@ int lgca_b200_destroy(lgca_b200_lattice* h)
     }
     for (int i = 0; i < 2; ++i) cudaFree(h->d_stage[i]);
     cudaFree(h->res_exch);
+    free_mv_buffers(h);
+    free_bf_buffers(h);
     cudaFree(h->snap_ghost); cudaFree(h->ns); cudaFree(h->sl); cudaFree(h->ch); cudaFree(h->xedge); cudaFree(h->d_flags);
     cudaFree(h->d_cell_density); cudaFree(h->d_cell_momentum); cudaFree(h->d_mean_density); cudaFree(h->d_mean_momentum);
     cudaFree(h->d_scalars); cudaFree(h->d_draws); cudaFree(h->d_draw_bytes);
@@ -661,6 +663,23 @@ int lgca_b200_body_force(lgca_b200_lattice* h, int forcing, const int32_t* draws
     int64_t remaining = (int64_t)(uint32_t)forcing; // the reference's unsigned compare (negative forcing = "no limit")
     bool first = true;
     int rc;
+    if (!g.halo && !(h->cfg.flags & LGCA_B200_FLAG_HOST_BODY_FORCE)) {
+        // whole lattice: everything on the device (first occurrences, gains, prefix sum, stop rule, scatter)
+        LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+        while (pos < n_draws && (first || remaining > 0)) {
+            const size_t batch = std::min<size_t>(n_draws - pos, (size_t)1 << 22);
+            size_t used = 0;
+            uint32_t rev = 0;
+            if ((rc = body_force_device(h, (uint32_t)remaining, first, draws + pos, batch, &used, &rev))) return rc;
+            pos += used;
+            remaining -= rev;
+            *reverted += rev;
+            first = false;
+            if (used < batch) break; // stopped on the count
+        }
+        *consumed = pos;
+        return 0;
+    }
     while (pos < n_draws && (first || remaining > 0)) {
         size_t batch = (size_t)std::max<int64_t>(4096, std::min<int64_t>(1 << 20, remaining * 12));
         batch = std::min(batch, n_draws - pos);

@@ -284,6 +284,20 @@ int lgca_b200_group_mean_velocity(lgca_b200_group* g, float out[2])
     return 0;
 }
 
+int lgca_b200_group_mean_velocity_exact(lgca_b200_group* g, float out[2])
+{
+    if (!g || !out) return set_error(LGCA_B200_EINVAL, "null argument");
+    float    sums[2] = {0.0f, 0.0f};
+    uint64_t cnt = 0;
+    for (lgca_b200_lattice* h : g->strips) { // strips are stored in y order = cell order
+        const int rc = lgca_b200_mean_velocity_exact(h, sums, &cnt);
+        if (rc) return rc;
+    }
+    out[0] = sums[0] / (float)cnt; // src/omp_lattice.cpp:553-554
+    out[1] = sums[1] / (float)cnt;
+    return 0;
+}
+
 // Exact body force over the strips (src/omp_lattice.cpp:254-346): the same batches as lgca_b200_body_force, with the
 // gather on every strip (0x80 = "not mine / not eligible"), an element-wise minimum, ONE ordered host replay, the apply on
 // every strip, and a republish of the edge rows when anything changed.

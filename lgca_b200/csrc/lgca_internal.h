@@ -98,6 +98,21 @@ struct lgca_b200_lattice {
     uint32_t*        res_exch;              // {word, tag} messages
     size_t           res_exch_words;
     uint32_t         res_epoch;             // message tags are monotonic across launches
+    // device-side exact body force (lgca_bodyforce.cu): draws, first-occurrence hash table, gains, block sums
+    int32_t*         d_bf_draws;
+    uint32_t*        d_bf_keys;
+    uint8_t*         d_bf_gain;
+    uint32_t*        d_bf_blocks;
+    size_t           bf_cap;
+    // order-exact mean velocity (lgca_mv.cu): rounding tables, per-segment summaries, class bytes + pinned mirrors
+    int32_t*         d_mv_tab;
+    int32_t*         d_mv_rec;
+    uint32_t*        d_mv_fluid;
+    uint8_t*         d_mv_cls;
+    int32_t*         h_mv_rec;
+    uint32_t*        h_mv_fluid;
+    uint8_t*         h_mv_cls;
+    uint64_t         mv_stats[4];           // segments taken as one integer add / walked cell by cell; ns on the device + copies / in the walk
 };
 
 namespace lgca_b200 {
@@ -127,6 +142,10 @@ int ring_wait_current_epoch(lgca_b200_lattice* h); // lgca_ring.cu: stream-order
 int ring_order_inplace_write(lgca_b200_lattice* h); // lgca_ring.cu: the compute stream waits for my last ghost-row push
 int unalias_snapshot(lgca_b200_lattice* h); // lgca_capi.cu: give the live state a buffer of its own before an in-place write
 int mean_velocity_sums(lgca_b200_lattice* h, double out3[3]); // lgca_capi.cu
+void free_mv_buffers(lgca_b200_lattice* h); // lgca_mv.cu
+void free_bf_buffers(lgca_b200_lattice* h); // lgca_bodyforce.cu
+int body_force_device(lgca_b200_lattice* h, uint32_t forcing, bool first, const int32_t* draws, size_t n, size_t* consumed,
+                      uint32_t* reverted); // lgca_bodyforce.cu: one batch, whole-lattice handles
 int steps_per_launch(const lgca_b200_lattice* h, int want); // lgca_capi.cu: steps ONE kernel launch can advance (<= want)
 inline int buffer_id(const lgca_b200_lattice* h, const uint32_t* p)
 {

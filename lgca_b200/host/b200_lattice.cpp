@@ -180,38 +180,43 @@ void B200_Lattice<model_>::post_process()
     ensure_on_device();
     const bool coarse = this->m_num_coarse_cells > 0 && this->m_dim_x % (2 * this->m_coarse_graining_radius) == 0 &&
                         this->m_dim_x >= 4 * this->m_coarse_graining_radius;
-    const int rc = lgca_b200_group_post_process(m_h, this->m_cell_density_cpu, this->m_cell_momentum_cpu,
+    const bool lazy = m_opt.lazy_cell_fields && this->m_cell_density_cpu;
+    const int rc = lgca_b200_group_post_process(m_h, lazy ? nullptr : this->m_cell_density_cpu, lazy ? nullptr : this->m_cell_momentum_cpu,
                                           coarse ? this->m_mean_density_cpu : nullptr,
                                           coarse ? this->m_mean_momentum_cpu : nullptr, m_opt.exact_post ? 1 : 0);
     if (rc) fail("post_process", rc);
-    m_fields_valid = true;
+    m_cell_fields_stale = lazy;
+}
+
+template <Model model_>
+void B200_Lattice<model_>::sync_cell_fields()
+{
+    if (!m_cell_fields_stale) return;
+    // the output buffer is unchanged since the post_process() that skipped them (a new snapshot is only taken by
+    // copy_data_to_output_buffer, which the tick schedule always follows with post_process)
+    const int rc = lgca_b200_group_post_process(m_h, this->m_cell_density_cpu, this->m_cell_momentum_cpu, nullptr, nullptr, 0);
+    if (rc) fail("sync_cell_fields", rc);
+    m_cell_fields_stale = false;
 }
 
 template <Model model_>
 std::vector<Real> B200_Lattice<model_>::get_mean_velocity()
 {
     std::vector<Real> mean_velocity(this->SPATIAL_DIM, 0.0);
-    if (this->m_cell_density_cpu && m_fields_valid) {
-        // the reference's loop at one thread (src/omp_lattice.cpp:508-557): sequential float32 sums over the
-        // per-cell host fields of the last post_process() -- the only order that reproduces its digits
-        Real sum_x = 0.0, sum_y = 0.0;
-        size_t counter = 0;
-        for (size_t n = 0; n < this->m_num_cells; ++n) {
-            if (this->m_cell_type_cpu[n] != CellType::FLUID) continue;
-            counter++;
-            const Real rho = this->m_cell_density_cpu[n];
-            if (rho > 1.0e-06) {
-                sum_x += this->m_cell_momentum_cpu[2 * n] / rho;
-                sum_y += this->m_cell_momentum_cpu[2 * n + 1] / rho;
-            }
-        }
-        mean_velocity[0] = sum_x / (Real)counter;
-        mean_velocity[1] = sum_y / (Real)counter;
-        return mean_velocity;
-    }
-    // no per-cell host fields (huge lattices): device reduction over the snapshot
     ensure_on_device();
     float out[2];
+    if (this->m_num_cells / (size_t)m_opt.n_gpus <= ((size_t)1 << 28)) {
+        // the reference's loop at one thread (src/omp_lattice.cpp:508-557): sequential float32 sums over the cells of
+        // the output buffer -- the only order that reproduces its digits and hence the forcing decisions of the pipe /
+        // Karman schedule.  The device reduces 1024-cell segments to integer summaries per float32 binade, the library
+        // walks them in order (csrc/lgca_mv.cu): bit-equal, without a pass over the per-cell host fields.
+        const int rc = lgca_b200_group_mean_velocity_exact(m_h, out);
+        if (rc) fail("get_mean_velocity", rc);
+        mean_velocity[0] = out[0];
+        mean_velocity[1] = out[1];
+        return mean_velocity;
+    }
+    // huge lattices (float32 sums saturate anyway): device reduction over the snapshot, double accumulation
     const int rc = lgca_b200_group_mean_velocity(m_h, out);
     if (rc) fail("get_mean_velocity", rc);
     mean_velocity[0] = out[0];

@@ -32,6 +32,8 @@ struct B200Options {
     std::vector<int> devices;  // explicit device ordinals of the strips (default: device, device+1, ...)
     int  k_fuse  = 0;     // time steps fused per HBM pass (0 = library default)
     bool cell_fields = true;  // produce per-cell density/momentum in post_process (needs 12 B/cell host+device)
+    bool lazy_cell_fields = false; // post_process() leaves the per-cell host fields alone (12 B/cell over PCIe per call);
+                                   // sync_cell_fields() computes them from the same output buffer when a writer asks
     bool exact_post  = true;  // reference summation order for the coarse momentum-y means
 };
 
@@ -51,6 +53,7 @@ public:
     std::vector<Real> get_mean_velocity() override;
     void apply_body_force(const int forcing) override;
     void post_process() override;
+    void sync_cell_fields() override;
     void copy_data_to_device() override;
     void copy_data_from_device() override;
     void copy_data_to_output_buffer() override;
@@ -71,7 +74,7 @@ private:
     B200Options        m_opt;
     lgca_b200_group*   m_h = nullptr;     // one lattice on n_gpus devices (n_gpus == 1: a plain whole-lattice handle)
     bool               m_on_device = false;   // host mirrors have been uploaded
-    bool               m_fields_valid = false;
+    bool               m_cell_fields_stale = false; // lazy mode: the last post_process() skipped the per-cell fields
     std::deque<int>    m_draws;               // rand() values drawn ahead for the body force, in stream order
     double             m_draws_per_hit = 8.0; // running estimate used to size the draw-ahead
 };

@@ -130,6 +130,9 @@ public:
     const uint8_t*  rnd_bits()    const { return m_rnd_cpu.ptr(); }
     char            bf_dir()      const { return m_bf_dir; }
     bool            has_cell_fields() const { return m_cell_density_cpu != nullptr && m_cell_momentum_cpu != nullptr; }
+    // Backends that fill the per-cell host fields lazily (B200Options::lazy_cell_fields) bring them up to date with
+    // the last post_process() here; writers call it before they read cell_density() / cell_momentum().
+    virtual void    sync_cell_fields() {}
     const string&   test_case()   const { return m_test_case; }
 
 private:

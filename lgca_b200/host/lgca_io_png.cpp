@@ -149,6 +149,7 @@ bool IoPng<model_>::write(const size_t step, const std::string dir)
     const bool mean = m_scalars.rfind("Mean", 0) == 0;
     const bool vec  = m_scalars.find("momentum") != std::string::npos;
     if (!mean && !cl->has_cell_fields()) return false;
+    if (!mean) m_lattice->sync_cell_fields();
     if (mean && cl->num_coarse_cells() == 0) return false;
     const unsigned w = mean ? cl->coarse_dim_x() : cl->dim_x(), h = mean ? cl->coarse_dim_y() : cl->dim_y();
     const Real* v = mean ? (vec ? cl->mean_momentum() : cl->mean_density()) : (vec ? cl->cell_momentum() : cl->cell_density());

@@ -65,6 +65,7 @@ void IoVti<model_>::write(const size_t step, const std::string dir)
     mean_file << dir << "mean_res_" << step << ".vti";
     const uint64_t n = m_lattice->num_cells(), nc = m_lattice->num_coarse_cells();
 
+    if (m_lattice->has_cell_fields()) m_lattice->sync_cell_fields();
     const Real* rho = m_lattice->has_cell_fields() ? m_lattice->cell_density() : nullptr;
     const Real* mom = m_lattice->has_cell_fields() ? m_lattice->cell_momentum() : nullptr;
     if (rho && mom) {
