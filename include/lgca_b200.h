@@ -60,8 +60,10 @@ enum {
                                                 of a call); A-B tests of the HBM-streaming wavefront kernel on small lattices */
     LGCA_B200_FLAG_FORCE_RESIDENT = 1u << 3, /* use the SM-resident kernel whenever the lattice fits on chip, also where the
                                                 library's own choice would be the wavefront kernel (A-B tests) */
-    LGCA_B200_FLAG_HOST_BODY_FORCE = 1u << 4 /* lgca_b200_body_force through gather -> host replay -> apply instead of the
+    LGCA_B200_FLAG_HOST_BODY_FORCE = 1u << 4,/* lgca_b200_body_force through gather -> host replay -> apply instead of the
                                                 device-side prefix (A-B tests; row strips always take this route) */
+    LGCA_B200_FLAG_RESIDENT_DYNAMIC = 1u << 5 /* SM-resident kernel: dynamic four-word groups instead of static word ownership
+                                                (A-B tests; the mapping of lattices with > 8192 words per CTA anyway) */
 };
 
 typedef struct lgca_b200_lattice lgca_b200_lattice; /* opaque */

@@ -13,6 +13,8 @@ FLAG_NO_CELL_FIELDS = 1 << 0
 FLAG_SIMPLE_KERNEL = 1 << 1
 FLAG_NO_RESIDENT = 1 << 2
 FLAG_FORCE_RESIDENT = 1 << 3
+FLAG_HOST_BODY_FORCE = 1 << 4
+FLAG_RESIDENT_DYNAMIC = 1 << 5
 
 # every symbol include/lgca_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [

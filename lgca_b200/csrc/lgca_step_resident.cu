@@ -24,6 +24,7 @@
 //     rows, which they sent after consuming block b (same argument as the multi-GPU ring, lgca_ring.cu).
 //   * Row ends: words are row-aligned here, so widths that are not a multiple of 32 only change where the carry bit
 //     of the x-shift comes from at the first / last word of a row.
+#include <stdio.h>
 #include <string.h>
 
 #include <algorithm>
@@ -56,6 +57,20 @@ struct ResArgs {
     int             rows_max; // rows of the shared-memory buffers = max strip height + 2H
     int             n_steps;
 };
+
+#ifdef LGCA_RES_TIMING
+// development aid (scripts/build_variant.sh x.so -DLGCA_RES_TIMING): cycles of CTA j's thread 0 in {poll, steps, publish, all}
+__device__ unsigned long long g_res_timing[160][4];
+#define RES_T(var) const long long var = clock64()
+#define RES_ACC(i, a, b) res_acc[i] += (unsigned long long)((b) - (a))
+#define RES_DECL unsigned long long res_acc[4] = {0, 0, 0, 0}
+#define RES_FLUSH do { if (tid == 0) for (int i = 0; i < 4; ++i) g_res_timing[j][i] += res_acc[i]; } while (0)
+#else
+#define RES_T(var) do { } while (0)
+#define RES_ACC(i, a, b) do { } while (0)
+#define RES_DECL do { } while (0)
+#define RES_FLUSH do { } while (0)
+#endif
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -168,9 +183,20 @@ __device__ __forceinline__ void plain4(uint32_t (&o)[4], const uint32_t* row, ui
     o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
 }
 
-template <int MODEL, bool HAS_NS, bool HAS_SL>
-__global__ void __launch_bounds__(RES_THREADS, 1) step_resident_kernel(const ResArgs A)
+// OWN selects the thread mapping of a step:
+//   OWN = 0: groups of four consecutive words (one LDS.128 / STS.128 per plane) handed out dynamically, e = tid, tid + T, ...;
+//            every step pays the (row, group) index arithmetic again (~170 instructions per word).
+//   OWN = S > 0: STATIC ownership -- thread t owns the words t, t + T, ... (at most S) of the CTA's local rows for the whole
+//            launch.  Word offsets, row-end flags, the row's hexagonal parity and the static masks of an owned word are
+//            computed / loaded ONCE and stay in registers; a step is a row-range test, the plane loads, the shifts, the
+//            LOP3 network and the stores.  Measured with clock64 (scripts/res_timing.py): the dynamic mapping spends
+//            ~1450 cycles per step on C1 (660 words per CTA: issue-bound on its own index arithmetic).
+template <int OWN> struct ResThreads { static constexpr int value = OWN > 0 ? 1024 : RES_THREADS; };
+
+template <int MODEL, bool HAS_NS, bool HAS_SL, int OWN>
+__global__ void __launch_bounds__(ResThreads<OWN>::value, 1) step_resident_kernel(const ResArgs A)
 {
+    constexpr int RES_THREADS = ResThreads<OWN>::value; // shadows the default inside the kernel
     constexpr int  ND  = num_dir_of(MODEL);
     constexpr bool HPP = rule_of(MODEL) == MODEL_HPP;
     constexpr int  NM  = (HPP ? 0 : 1) + (HAS_NS ? 1 : 0) + (HAS_SL ? 1 : 0); // static mask planes held on chip
@@ -228,6 +254,33 @@ __global__ void __launch_bounds__(RES_THREADS, 1) step_resident_kernel(const Res
     const int PG = P / 4, gl = (nw - 1) / 4;                 // groups per row; group that holds the last real word
     const int dq = RES_THREADS / PG, dr = RES_THREADS % PG;
     const int q0 = tid / PG, g0 = tid % PG;
+    // static ownership: word offset inside a plane, local row (-1 = slot unused), flags {first word, last word, odd row,
+    // N/S domain-edge row, pre-shift of the partial last word << 8} and the static masks of every owned word
+    constexpr int OWN_N = OWN > 0 ? OWN : 1;
+    uint32_t own_off[OWN_N], own_flg[OWN_N], own_ch[HPP ? 1 : OWN_N], own_ns[HAS_NS ? OWN_N : 1], own_sl[HAS_SL ? OWN_N : 1],
+        own_ew[HAS_SL ? OWN_N : 1];
+    int own_row[OWN_N];
+    if constexpr (OWN > 0) {
+#pragma unroll
+        for (int i = 0; i < OWN; ++i) {
+            const int e = tid + i * RES_THREADS;
+            const int r = e / nw, w = e - r * nw;
+            const bool valid = r >= 1 && r < LR - 1; // rows 0 and LR-1 are never recomputed (their neighbours lie outside)
+            own_row[i] = valid ? r : -1;
+            own_off[i] = (uint32_t)(r * P + w);
+            uint32_t f = (w == 0 ? 1u : 0u) | (w == nw - 1 ? 2u : 0u) | (((uint32_t)r & 1u) << 2) | ((w == 0 && rem) ? (32u - (uint32_t)rem) << 8 : 0u);
+            if (!HPP) own_ch[HPP ? 0 : i] = valid ? m_ch[own_off[i]] : 0u;
+            if (HAS_NS) own_ns[HAS_NS ? i : 0] = valid ? m_ns[own_off[i]] : 0u;
+            if (HAS_SL) {
+                own_sl[HAS_SL ? i : 0] = valid ? m_sl[own_off[i]] : 0u;
+                own_ew[HAS_SL ? i : 0] = valid ? __ldg(A.xedge + w) : 0u;
+                int gy = y0 - H + r;
+                if (gy < 0) gy += (int)A.rows; else if (gy >= (int)A.rows) gy -= (int)A.rows;
+                if ((uint32_t)gy == A.dim_y_south || (uint32_t)gy == A.dim_y_north) f |= 8u;
+            }
+            own_flg[i] = f;
+        }
+    }
     const uint32_t hi_last = rem ? (uint32_t)rem - 1u : 31u;
     const uint32_t vm_last = rem ? ((1u << rem) - 1u) : 0xFFFFFFFFu;
 
@@ -235,107 +288,182 @@ __global__ void __launch_bounds__(RES_THREADS, 1) step_resident_kernel(const Res
     uint32_t* nxt = buf1;
     const int n_blocks = (A.n_steps + A.K - 1) / A.K;
     const int lower = (j + A.G - 1) % A.G, upper = (j + 1) % A.G;
-    const int    side_n   = ND * H * nw;                            // messages of one side of one CTA
+    // Exchange area: [block parity][CTA][side][plane][H rows x P words] of {word, tag}.  A segment (one plane of one side)
+    // mirrors H consecutive rows of the shared-memory plane, padding words included, so a message index inside a segment
+    // is also the word offset at the destination: no index arithmetic per message.  Warps are dealt round-robin to the
+    // 2 * ND segments (warp -> segment and chunk are computed once), lanes run over the segment's messages.
+    const int    seg_n    = H * P;                                  // messages of one segment
+    const int    side_n   = ND * seg_n;                             // messages of one side of one CTA
     const size_t parity_n = (size_t)A.G * 2 * side_n;
     constexpr int NWARPS = RES_THREADS / 32;
+    constexpr int NSEG   = 2 * ND;
+    static_assert(NWARPS >= NSEG, "one warp per exchange segment at least");
+    const int x_seg = warp % NSEG, x_chunk = warp / NSEG;           // my segment, my first 32-message chunk in it
+    const int x_nchunk = NWARPS / NSEG + (x_seg < NWARPS % NSEG ? 1 : 0); // warps sharing my segment
+    const int x_half = x_seg / ND, x_d = x_seg % ND;                // 0: bottom side / lower ghost rows, 1: top / upper
 
+    RES_DECL;
+    RES_T(t_all0);
     for (int b = 0; b < n_blocks; ++b) {
         const int kb = min(A.K, A.n_steps - b * A.K);
+        RES_T(t_p0);
         if (b > 0) {
             // ghost rows of this block = the neighbours' edge rows after block b-1: poll every message until its tag
             // shows.  One warp per (side, plane, row): consecutive lanes read consecutive 8-byte messages.
             const uint32_t tag = A.epoch_base + (uint32_t)b;
             const uint2* ex = A.exch + (size_t)((b - 1) & 1) * parity_n;
-            for (int rr = warp; rr < 2 * ND * H; rr += NWARPS) {
-                const int half = rr >= ND * H, i = half ? rr - ND * H : rr, d = i / H, row = i - d * H;
-                // lower ghost rows [0, H) <- the lower neighbour's TOP side; upper ghost rows <- the upper neighbour's BOTTOM side
-                const uint2* src = ex + ((size_t)(half ? upper : lower) * 2 + (half ? 0 : 1)) * side_n + (size_t)i * nw;
-                uint32_t* dst = cur + d * plane_sz + (size_t)((half ? H + R : 0) + row) * P;
-                for (int w = lane; w < nw; w += 32) {
-                    uint2 m;
-                    do { m = ld_msg(src + w); } while (m.y != tag);
-                    dst[w] = m.x;
+            // lower ghost rows [0, H) <- the lower neighbour's TOP side; upper ghost rows [H+R, LR) <- the upper neighbour's BOTTOM side
+            const uint2* src = ex + ((size_t)(x_half ? upper : lower) * 2 + (x_half ? 0 : 1)) * side_n + (size_t)x_d * seg_n;
+            uint32_t*    dst = cur + x_d * plane_sz + (size_t)(x_half ? H + R : 0) * P;
+            // up to RES_POLL loads in flight per thread: the exchange costs about one L2 round trip per batch
+            constexpr int RES_POLL = 8;
+            for (int m0 = x_chunk * 32 + lane; m0 < seg_n; m0 += x_nchunk * 32 * RES_POLL) {
+                uint2 v[RES_POLL];
+#pragma unroll
+                for (int q = 0; q < RES_POLL; ++q) {
+                    const int m = m0 + q * x_nchunk * 32;
+                    v[q] = make_uint2(0u, tag);
+                    if (m < seg_n) v[q] = ld_msg(src + m);
+                }
+                // poll in rounds: every message still missing is re-loaded in the same round (sequential per-message
+                // polling costs one L2 round trip per message: scripts/dbg/pingpong.cu, 4 messages per thread 3x slower)
+                bool missing;
+                do {
+                    missing = false;
+#pragma unroll
+                    for (int q = 0; q < RES_POLL; ++q) {
+                        if (v[q].y != tag) { v[q] = ld_msg(src + m0 + q * x_nchunk * 32); missing = true; }
+                    }
+                } while (missing);
+#pragma unroll
+                for (int q = 0; q < RES_POLL; ++q) {
+                    const int m = m0 + q * x_nchunk * 32;
+                    if (m < seg_n) dst[m] = v[q].x;
                 }
             }
             __syncthreads();
         }
+        RES_T(t_p1);
+        RES_ACC(0, t_p0, t_p1);
         for (int s = 1; s <= kb; ++s) {
             // rows that are still needed and still valid after step s of this block
             const int ra = H - (kb - s), rb = H + R + (kb - s);
-            const int total = (rb - ra) * PG;
-            int r = ra + q0, g = g0;
-            for (int e = tid; e < total; e += RES_THREADS) {
-                const uint32_t rc = (uint32_t)r * P, rs = rc - P, rn = rc + P, g4 = 4u * (uint32_t)g;
-                GroupCtx c;
-                c.lastg     = g >= gl;
-                c.il        = (nw - 1) - 4 * gl;
-                c.hi        = hi_last;
-                c.left_off  = g == 0 ? (uint32_t)nw - 1u : g4 - 1u;
-                c.lsh       = (g == 0 && rem) ? 32u - (uint32_t)rem : 0u;
-                c.right_off = g4 + 4u;
-                uint32_t in[7][4];
-                if (HPP) {
-                    shift_up4(in[0], cur + 0 * plane_sz + rc, g4, c, 1u);
-                    shift_down4(in[2], cur + 2 * plane_sz + rc, g4, c, 1u);
-                    plain4(in[1], cur + 1 * plane_sz + rs, g4);
-                    plain4(in[3], cur + 3 * plane_sz + rn, g4);
-                } else {
-                    // odd/even hexagonal rows, branch-free: even rows shift planes 1 and 5 up, odd rows shift planes 2 and
-                    // 4 down; local parity == global parity (strip starts and H are even); a funnel shift by 0 passes through
-                    const uint32_t odd = (uint32_t)r & 1u, even = odd ^ 1u;
-                    shift_up4(in[0], cur + 0 * plane_sz + rc, g4, c, 1u);
-                    shift_down4(in[3], cur + 3 * plane_sz + rc, g4, c, 1u);
-                    shift_up4(in[1], cur + 1 * plane_sz + rs, g4, c, even);
-                    shift_down4(in[2], cur + 2 * plane_sz + rs, g4, c, odd);
-                    shift_down4(in[4], cur + 4 * plane_sz + rn, g4, c, odd);
-                    shift_up4(in[5], cur + 5 * plane_sz + rn, g4, c, even);
-                    if (ND == 7) plain4(in[6], cur + 6 * plane_sz + rc, g4);
+            if constexpr (OWN > 0) {
+#pragma unroll
+                for (int i = 0; i < OWN; ++i) {
+                    if (own_row[i] < ra || own_row[i] >= rb) continue;
+                    const uint32_t f = own_flg[i], o = own_off[i];
+                    const bool     firstw = f & 1u, lastw = f & 2u;
+                    const uint32_t odd = (f >> 2) & 1u, even = odd ^ 1u, lsh = f >> 8;
+                    const uint32_t ol = firstw ? o + (uint32_t)nw - 1u : o - 1u;  // word left / right of mine (periodic)
+                    const uint32_t orr = lastw ? o - ((uint32_t)nw - 1u) : o + 1u;
+                    // site x <- site x-1 / site x+1 by sh (0 or 1) sites; dr = row displacement in words
+                    auto up = [&](const uint32_t* pl, int dr, uint32_t sh) { return __funnelshift_l(pl[(int)ol + dr] << lsh, pl[(int)o + dr], sh); };
+                    auto down = [&](const uint32_t* pl, int dr, uint32_t sh) {
+                        const uint32_t v = pl[(int)o + dr], nb = pl[(int)orr + dr];
+                        return lastw ? ((v >> sh) | ((nb & sh) << hi_last)) : __funnelshift_r(v, nb, sh);
+                    };
+                    uint32_t n[7] = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
+                    if (HPP) {
+                        n[0] = up(cur + 0 * plane_sz, 0, 1u);
+                        n[2] = down(cur + 2 * plane_sz, 0, 1u);
+                        n[1] = cur[1 * plane_sz + o - P];
+                        n[3] = cur[3 * plane_sz + o + P];
+                    } else {
+                        n[0] = up(cur + 0 * plane_sz, 0, 1u);
+                        n[3] = down(cur + 3 * plane_sz, 0, 1u);
+                        n[1] = up(cur + 1 * plane_sz, -P, even);
+                        n[2] = down(cur + 2 * plane_sz, -P, odd);
+                        n[4] = down(cur + 4 * plane_sz, P, odd);
+                        n[5] = up(cur + 5 * plane_sz, P, even);
+                        if (ND == 7) n[6] = cur[6 * plane_sz + o];
+                    }
+                    collide_and_walls<MODEL, HAS_NS, HAS_SL>(n, HPP ? 0u : own_ch[HPP ? 0 : i], HAS_NS ? own_ns[HAS_NS ? i : 0] : 0u,
+                                                             HAS_SL ? own_sl[HAS_SL ? i : 0] : 0u, HAS_SL ? own_ew[HAS_SL ? i : 0] : 0u,
+                                                             (f & 8u) ? 0xFFFFFFFFu : 0u);
+                    const uint32_t vm = lastw ? vm_last : 0xFFFFFFFFu;
+#pragma unroll
+                    for (int d = 0; d < ND; ++d) nxt[d * plane_sz + o] = n[d] & vm;
                 }
-                uint32_t pch[4] = {0u, 0u, 0u, 0u}, pns[4] = {0u, 0u, 0u, 0u}, psl[4] = {0u, 0u, 0u, 0u}, pew[4] = {0u, 0u, 0u, 0u};
-                if (!HPP) plain4(pch, m_ch + rc, g4);
-                if (HAS_NS) plain4(pns, m_ns + rc, g4);
-                uint32_t ns_row = 0u;
-                if (HAS_SL) {
-                    plain4(psl, m_sl + rc, g4);
-                    const uint4 ev = __ldg(reinterpret_cast<const uint4*>(A.xedge + g4));
-                    pew[0] = ev.x; pew[1] = ev.y; pew[2] = ev.z; pew[3] = ev.w;
-                    int gy = y0 - H + r;                              // global (stored) row of this local row
-                    if (gy < 0) gy += (int)A.rows; else if (gy >= (int)A.rows) gy -= (int)A.rows;
-                    ns_row = ((uint32_t)gy == A.dim_y_south || (uint32_t)gy == A.dim_y_north) ? 0xFFFFFFFFu : 0u;
+            } else {
+                const int total = (rb - ra) * PG;
+                int r = ra + q0, g = g0;
+                for (int e = tid; e < total; e += RES_THREADS) {
+                    const uint32_t rc = (uint32_t)r * P, rs = rc - P, rn = rc + P, g4 = 4u * (uint32_t)g;
+                    GroupCtx c;
+                    c.lastg     = g >= gl;
+                    c.il        = (nw - 1) - 4 * gl;
+                    c.hi        = hi_last;
+                    c.left_off  = g == 0 ? (uint32_t)nw - 1u : g4 - 1u;
+                    c.lsh       = (g == 0 && rem) ? 32u - (uint32_t)rem : 0u;
+                    c.right_off = g4 + 4u;
+                    uint32_t in[7][4];
+                    if (HPP) {
+                        shift_up4(in[0], cur + 0 * plane_sz + rc, g4, c, 1u);
+                        shift_down4(in[2], cur + 2 * plane_sz + rc, g4, c, 1u);
+                        plain4(in[1], cur + 1 * plane_sz + rs, g4);
+                        plain4(in[3], cur + 3 * plane_sz + rn, g4);
+                    } else {
+                        // odd/even hexagonal rows, branch-free: even rows shift planes 1 and 5 up, odd rows shift planes 2 and
+                        // 4 down; local parity == global parity (strip starts and H are even); a funnel shift by 0 passes through
+                        const uint32_t odd = (uint32_t)r & 1u, even = odd ^ 1u;
+                        shift_up4(in[0], cur + 0 * plane_sz + rc, g4, c, 1u);
+                        shift_down4(in[3], cur + 3 * plane_sz + rc, g4, c, 1u);
+                        shift_up4(in[1], cur + 1 * plane_sz + rs, g4, c, even);
+                        shift_down4(in[2], cur + 2 * plane_sz + rs, g4, c, odd);
+                        shift_down4(in[4], cur + 4 * plane_sz + rn, g4, c, odd);
+                        shift_up4(in[5], cur + 5 * plane_sz + rn, g4, c, even);
+                        if (ND == 7) plain4(in[6], cur + 6 * plane_sz + rc, g4);
+                    }
+                    uint32_t pch[4] = {0u, 0u, 0u, 0u}, pns[4] = {0u, 0u, 0u, 0u}, psl[4] = {0u, 0u, 0u, 0u}, pew[4] = {0u, 0u, 0u, 0u};
+                    if (!HPP) plain4(pch, m_ch + rc, g4);
+                    if (HAS_NS) plain4(pns, m_ns + rc, g4);
+                    uint32_t ns_row = 0u;
+                    if (HAS_SL) {
+                        plain4(psl, m_sl + rc, g4);
+                        const uint4 ev = __ldg(reinterpret_cast<const uint4*>(A.xedge + g4));
+                        pew[0] = ev.x; pew[1] = ev.y; pew[2] = ev.z; pew[3] = ev.w;
+                        int gy = y0 - H + r;                              // global (stored) row of this local row
+                        if (gy < 0) gy += (int)A.rows; else if (gy >= (int)A.rows) gy -= (int)A.rows;
+                        ns_row = ((uint32_t)gy == A.dim_y_south || (uint32_t)gy == A.dim_y_north) ? 0xFFFFFFFFu : 0u;
+                    }
+                    uint32_t out[7][4];
+    #pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        uint32_t n[7];
+    #pragma unroll
+                        for (int d = 0; d < 7; ++d) n[d] = d < ND ? in[d][i] : 0u;
+                        collide_and_walls<MODEL, HAS_NS, HAS_SL>(n, pch[i], pns[i], psl[i], pew[i], ns_row);
+                        // words after the last real word are padding (kept zero), the last real word may be partial
+                        const uint32_t vm = !c.lastg ? 0xFFFFFFFFu : (i < c.il ? 0xFFFFFFFFu : (i == c.il ? vm_last : 0u));
+    #pragma unroll
+                        for (int d = 0; d < ND; ++d) out[d][i] = n[d] & vm;
+                    }
+    #pragma unroll
+                    for (int d = 0; d < ND; ++d) sts4(nxt + d * plane_sz + rc + g4, make_uint4(out[d][0], out[d][1], out[d][2], out[d][3]));
+                    r += dq; g += dr;
+                    if (g >= PG) { g -= PG; ++r; }
                 }
-                uint32_t out[7][4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    uint32_t n[7];
-#pragma unroll
-                    for (int d = 0; d < 7; ++d) n[d] = d < ND ? in[d][i] : 0u;
-                    collide_and_walls<MODEL, HAS_NS, HAS_SL>(n, pch[i], pns[i], psl[i], pew[i], ns_row);
-                    // words after the last real word are padding (kept zero), the last real word may be partial
-                    const uint32_t vm = !c.lastg ? 0xFFFFFFFFu : (i < c.il ? 0xFFFFFFFFu : (i == c.il ? vm_last : 0u));
-#pragma unroll
-                    for (int d = 0; d < ND; ++d) out[d][i] = n[d] & vm;
-                }
-#pragma unroll
-                for (int d = 0; d < ND; ++d) sts4(nxt + d * plane_sz + rc + g4, make_uint4(out[d][0], out[d][1], out[d][2], out[d][3]));
-                r += dq; g += dr;
-                if (g >= PG) { g -= PG; ++r; }
             }
             __syncthreads();
             uint32_t* t = cur; cur = nxt; nxt = t;
         }
+        RES_T(t_p2);
+        RES_ACC(1, t_p1, t_p2);
         if (b + 1 < n_blocks) {
             // publish my edge rows for the neighbours' next block (the last step ended with a __syncthreads)
             const uint32_t tag = A.epoch_base + (uint32_t)b + 1u;
-            uint2* ex = A.exch + (size_t)(b & 1) * parity_n + (size_t)j * 2 * side_n;
-            for (int rr = warp; rr < 2 * ND * H; rr += NWARPS) {
-                const int side = rr >= ND * H, i = side ? rr - ND * H : rr, d = i / H, row = i - d * H;
-                // side 0 = BOTTOM: my lowest H owned rows [H, 2H); side 1 = TOP: my highest H owned rows [R, R+H)
-                const uint32_t* src = cur + d * plane_sz + (size_t)((side ? R : H) + row) * P;
-                uint2* dst = ex + (size_t)rr * nw;
-                for (int w = lane; w < nw; w += 32) st_msg(dst + w, src[w], tag);
-            }
+            // side 0 = BOTTOM: my lowest H owned rows [H, 2H); side 1 = TOP: my highest H owned rows [R, R+H)
+            uint2*          dst = A.exch + (size_t)(b & 1) * parity_n + ((size_t)j * 2 + x_half) * side_n + (size_t)x_d * seg_n;
+            const uint32_t* src = cur + x_d * plane_sz + (size_t)(x_half ? R : H) * P;
+            for (int m = x_chunk * 32 + lane; m < seg_n; m += x_nchunk * 32) st_msg(dst + m, src[m], tag);
         }
+        RES_T(t_p3);
+        RES_ACC(2, t_p2, t_p3);
     }
+    RES_T(t_all1);
+    RES_ACC(3, t_all0, t_all1);
+    RES_FLUSH;
     // ---- write the strip back: TMA bulk stores -------------------------------------------------------------------
     if (tid == 0) {
         fence_proxy_async(); // the st.shared of the last step -> visible to the bulk stores
@@ -350,7 +478,7 @@ __global__ void __launch_bounds__(RES_THREADS, 1) step_resident_kernel(const Res
 // ---- planning ----------------------------------------------------------------------------------------------------
 struct ResPlan {
     int    ok;
-    int    G, unit, base_units, extra_units, H, K, rows_max;
+    int    G, unit, base_units, extra_units, H, K, rows_max, own;
     size_t smem_bytes, exch_words;
 };
 
@@ -386,7 +514,12 @@ static ResPlan res_plan(const lgca_b200_lattice* h)
         p.ok = 1; p.G = G; p.unit = unit; p.base_units = base; p.extra_units = extra; p.H = H; p.K = K;
         p.rows_max = r_max + 2 * H;
         p.smem_bytes = smem;
-        p.exch_words = (size_t)2 * G * 2 * nd * H * g.nw * 2; // {word, tag} messages
+        p.exch_words = (size_t)2 * G * 2 * nd * H * g.pitch * 2; // {word, tag} messages
+        // thread mapping: static ownership while a thread owns at most 8 words of the CTA's local rows, else dynamic groups
+        const size_t words = (size_t)p.rows_max * g.nw;
+        const int    per_thread = (int)((words + 1023) / 1024);
+        p.own = per_thread <= 1 ? 1 : (per_thread <= 2 ? 2 : (per_thread <= 4 ? 4 : (per_thread <= 8 ? 8 : 0)));
+        if (h->cfg.flags & LGCA_B200_FLAG_RESIDENT_DYNAMIC) p.own = 0;
         return p;
     }
     return p;
@@ -394,16 +527,39 @@ static ResPlan res_plan(const lgca_b200_lattice* h)
 
 bool resident_supported(const lgca_b200_lattice* h) { return res_plan(h).ok != 0; }
 
-template <int MODEL, bool NS, bool SL>
-static int launch_res_variant(lgca_b200_lattice* h, const ResPlan& p, ResArgs& A, cudaStream_t s, bool prepare_only)
+template <int MODEL, bool NS, bool SL, int OWN>
+static int launch_res_own(lgca_b200_lattice* h, const ResPlan& p, ResArgs& A, cudaStream_t s, bool prepare_only)
 {
-    auto kernel = step_resident_kernel<MODEL, NS, SL>;
+    auto kernel = step_resident_kernel<MODEL, NS, SL, OWN>;
     LGCA_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)RES_MAX_SMEM - 1024));
     if (prepare_only) return 0;
     void* args[] = {(void*)&A};
-    LGCA_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kernel, dim3(p.G, 1, 1), dim3(RES_THREADS, 1, 1), args, p.smem_bytes, s));
+    LGCA_CUDA_CHECK(cudaLaunchCooperativeKernel((const void*)kernel, dim3(p.G, 1, 1), dim3(ResThreads<OWN>::value, 1, 1), args,
+                                                p.smem_bytes, s));
     h->launches++;
     return 0;
+}
+
+template <int MODEL, bool NS, bool SL>
+static int launch_res_variant(lgca_b200_lattice* h, const ResPlan& p, ResArgs& A, cudaStream_t s, bool prepare_only)
+{
+#define RES_GO(OWN) launch_res_own<MODEL, NS, SL, OWN>(h, p, A, s, prepare_only)
+    if (prepare_only) { // every mapping gets its shared-memory opt-in
+        int rc = RES_GO(0);
+        if (!rc) rc = RES_GO(1);
+        if (!rc) rc = RES_GO(2);
+        if (!rc) rc = RES_GO(4);
+        if (!rc) rc = RES_GO(8);
+        return rc;
+    }
+    switch (p.own) {
+    case 1: return RES_GO(1);
+    case 2: return RES_GO(2);
+    case 4: return RES_GO(4);
+    case 8: return RES_GO(8);
+    default: return RES_GO(0);
+    }
+#undef RES_GO
 }
 
 template <int MODEL>
@@ -446,6 +602,20 @@ int launch_step_resident(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out
     }
     if (rc) return rc;
     if (in) h->res_epoch += (uint32_t)((n_steps + p.K - 1) / p.K); // counters are monotonic across launches
+#ifdef LGCA_RES_TIMING
+    if (in && n_steps >= 100) {
+        static unsigned long long host_t[160][4];
+        cudaStreamSynchronize(s);
+        cudaMemcpyFromSymbol(host_t, g_res_timing, sizeof(host_t));
+        unsigned long long z[160][4] = {};
+        cudaMemcpyToSymbol(g_res_timing, z, sizeof(z));
+        fprintf(stderr, "res timing G=%d K=%d H=%d own=%d steps=%d: cycles/step of CTA 0 / G/2 / G-1: ", p.G, p.K, p.H, p.own, n_steps);
+        for (int j : {0, p.G / 2, p.G - 1})
+            fprintf(stderr, "[poll %.0f steps %.0f publish %.0f all %.0f] ", (double)host_t[j][0] / n_steps, (double)host_t[j][1] / n_steps,
+                    (double)host_t[j][2] / n_steps, (double)host_t[j][3] / n_steps);
+        fprintf(stderr, "\n");
+    }
+#endif
     return 0;
 }
 

@@ -23,8 +23,13 @@ KS = [int(a) for a in sys.argv[1:]] or [0]
 print("| lattice | kernel | k | us/update @5 | us/update @100 | us/update @1000 | site updates/s @1000 |")
 print("|---|---|---:|---:|---:|---:|---:|")
 for name, model, dx, dy, bc in CONFIGS:
-    for kernel, flags in ((("resident", FLAG_FORCE_RESIDENT),) if os.environ.get("SMALL_ONLY_RESIDENT") else (("wave", FLAG_NO_RESIDENT), ("resident", FLAG_FORCE_RESIDENT))):
-        for k in (KS if kernel == "resident" else [0]):
+    kernels = [("wave", FLAG_NO_RESIDENT), ("resident", FLAG_FORCE_RESIDENT)]
+    if os.environ.get("SMALL_WPT"):  # A-B of the 1-word / 4-word variants of the resident kernel
+        kernels = [("resident static", FLAG_FORCE_RESIDENT), ("resident dynamic", FLAG_FORCE_RESIDENT | 32)]
+    elif os.environ.get("SMALL_ONLY_RESIDENT"):
+        kernels = kernels[1:]
+    for kernel, flags in kernels:
+        for k in (KS if kernel.startswith("resident") else [0]):
             e = lgca_b200.Engine(model, dx, dy, k_fuse=k, flags=flags | FLAG_NO_CELL_FIELDS)
             e.apply_bc_device(bc)
             e.init_random_device(1)

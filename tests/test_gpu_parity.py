@@ -35,7 +35,10 @@ VARIANTS = [pytest.param(dict(flags=2), id="simple"), pytest.param(dict(k_fuse=1
             pytest.param(dict(flags=4), id="default"),
             pytest.param(dict(k_fuse=1, flags=8), id="res1"), pytest.param(dict(k_fuse=2, flags=8), id="res2"),
             pytest.param(dict(k_fuse=3, flags=8), id="res3"), pytest.param(dict(k_fuse=5, flags=8), id="res5"),
-            pytest.param(dict(flags=8), id="res"), pytest.param(dict(), id="auto")]
+            pytest.param(dict(flags=8), id="res"), pytest.param(dict(), id="auto"),
+            # 32: the resident kernel's dynamic four-word-group mapping instead of static word ownership
+            pytest.param(dict(k_fuse=1, flags=8 | 32), id="res1-dyn"), pytest.param(dict(k_fuse=4, flags=8 | 32), id="res4-dyn"),
+            pytest.param(dict(flags=8 | 32), id="res-dyn")]
 
 
 @pytest.mark.parametrize("variant", VARIANTS)
