@@ -19,8 +19,6 @@ struct WavePlan {
     int edge_rows;  // strips: rows of the bottom / top edge chunk (0 = uniform chunks)
     int chunks;     // chunks over the stored rows
     int tiles;      // bands * chunks = warps launched
-    int tail_chunks; // whole lattices: the LAST tail_chunks chunks are only tail_rows high -- they are dispatched last and
-    int tail_rows;   // fill the schedulers that the staggered finish of a single round of full chunks leaves idle
 };
 } // namespace lgca_b200
 

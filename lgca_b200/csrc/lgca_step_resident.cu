@@ -301,6 +301,9 @@ __global__ void __launch_bounds__(ResThreads<OWN>::value, 1) step_resident_kerne
     const int x_seg = warp % NSEG, x_chunk = warp / NSEG;           // my segment, my first 32-message chunk in it
     const int x_nchunk = NWARPS / NSEG + (x_seg < NWARPS % NSEG ? 1 : 0); // warps sharing my segment
     const int x_half = x_seg / ND, x_d = x_seg % ND;                // 0: bottom side / lower ghost rows, 1: top / upper
+    const int x_stride = x_nchunk * 32, x_m0 = x_chunk * 32 + lane; // my messages of a segment: x_m0 + q * x_stride < seg_n
+    const int x_nmine = x_m0 < seg_n ? (seg_n - x_m0 + x_stride - 1) / x_stride : 0;
+    const int x_n0 = (seg_n - x_chunk * 32 + x_stride - 1) / x_stride; // ... of lane 0 (never fewer than any other lane's)
 
     RES_DECL;
     RES_T(t_all0);
@@ -315,31 +318,35 @@ __global__ void __launch_bounds__(ResThreads<OWN>::value, 1) step_resident_kerne
             // lower ghost rows [0, H) <- the lower neighbour's TOP side; upper ghost rows [H+R, LR) <- the upper neighbour's BOTTOM side
             const uint2* src = ex + ((size_t)(x_half ? upper : lower) * 2 + (x_half ? 0 : 1)) * side_n + (size_t)x_d * seg_n;
             uint32_t*    dst = cur + x_d * plane_sz + (size_t)(x_half ? H + R : 0) * P;
-            // up to RES_POLL loads in flight per thread: the exchange costs about one L2 round trip per batch
-            constexpr int RES_POLL = 8;
-            for (int m0 = x_chunk * 32 + lane; m0 < seg_n; m0 += x_nchunk * 32 * RES_POLL) {
-                uint2 v[RES_POLL];
+            // Waiting: ONE lane per warp polls ONE sentinel message (the last one the sender's warp of the same index stored),
+            // with a short back-off -- 148 x 1024 threads polling all their messages would ask L2 for more than it can
+            // deliver and delay the very stores they wait for.  Then every thread loads its messages (four in flight) and
+            // re-polls only the ones whose tag has not arrived yet (stores may overtake each other).  The loop is kept lean
+            // on purpose: ncu showed an 8-way unrolled version of it issuing more instructions than the steps themselves.
+            if (lane == 0 && x_n0 > 0) {
+                const uint2* sentinel = src + x_m0 - lane + (x_n0 - 1) * x_stride;
+                while (ld_msg(sentinel).y != tag) __nanosleep(32);
+            }
+            __syncwarp();
+            const uint2* sp = src + x_m0;
+            uint32_t*    dp = dst + x_m0;
+            for (int q0 = 0; q0 < x_nmine; q0 += 4) {
+                uint2 v[4];
 #pragma unroll
-                for (int q = 0; q < RES_POLL; ++q) {
-                    const int m = m0 + q * x_nchunk * 32;
+                for (int q = 0; q < 4; ++q) {
                     v[q] = make_uint2(0u, tag);
-                    if (m < seg_n) v[q] = ld_msg(src + m);
+                    if (q0 + q < x_nmine) v[q] = ld_msg(sp + (q0 + q) * x_stride);
                 }
-                // poll in rounds: every message still missing is re-loaded in the same round (sequential per-message
-                // polling costs one L2 round trip per message: scripts/dbg/pingpong.cu, 4 messages per thread 3x slower)
                 bool missing;
                 do {
                     missing = false;
 #pragma unroll
-                    for (int q = 0; q < RES_POLL; ++q) {
-                        if (v[q].y != tag) { v[q] = ld_msg(src + m0 + q * x_nchunk * 32); missing = true; }
-                    }
+                    for (int q = 0; q < 4; ++q)
+                        if (v[q].y != tag) { v[q] = ld_msg(sp + (q0 + q) * x_stride); missing = true; }
                 } while (missing);
 #pragma unroll
-                for (int q = 0; q < RES_POLL; ++q) {
-                    const int m = m0 + q * x_nchunk * 32;
-                    if (m < seg_n) dst[m] = v[q].x;
-                }
+                for (int q = 0; q < 4; ++q)
+                    if (q0 + q < x_nmine) dp[(q0 + q) * x_stride] = v[q].x;
             }
             __syncthreads();
         }
@@ -456,7 +463,7 @@ __global__ void __launch_bounds__(ResThreads<OWN>::value, 1) step_resident_kerne
             // side 0 = BOTTOM: my lowest H owned rows [H, 2H); side 1 = TOP: my highest H owned rows [R, R+H)
             uint2*          dst = A.exch + (size_t)(b & 1) * parity_n + ((size_t)j * 2 + x_half) * side_n + (size_t)x_d * seg_n;
             const uint32_t* src = cur + x_d * plane_sz + (size_t)(x_half ? R : H) * P;
-            for (int m = x_chunk * 32 + lane; m < seg_n; m += x_nchunk * 32) st_msg(dst + m, src[m], tag);
+            for (int q = 0; q < x_nmine; ++q) st_msg(dst + x_m0 + q * x_stride, src[x_m0 + q * x_stride], tag);
         }
         RES_T(t_p3);
         RES_ACC(2, t_p2, t_p3);
@@ -489,40 +496,60 @@ static ResPlan res_plan(const lgca_b200_lattice* h)
     const Geom& g = h->g;
     if (g.halo != 0 || !g.wrap_y) return p;                       // whole lattices only
     if (h->cfg.flags & (LGCA_B200_FLAG_SIMPLE_KERNEL | LGCA_B200_FLAG_NO_RESIDENT)) return p;
-    // Where it pays (measured on B200, profiles/r02_small_lattices.md): every width that is not a multiple of 32 (the
-    // wavefront kernel's irregular-width variant is 2-3x slower than its regular one) and regular lattices below ~6 M
-    // sites, where the wavefront kernel cannot fill the machine.  Above that the wavefront kernel's K-step register
-    // blocking wins (HPP 4096^2, FHP-II 4096x2048).  LGCA_B200_FLAG_FORCE_RESIDENT overrides (A-B tests).
-    if (!(h->cfg.flags & LGCA_B200_FLAG_FORCE_RESIDENT) && g.rem == 0 && (uint64_t)g.dim_x * g.rows >= 6000000ull) return p;
+    // Used wherever the lattice fits on chip (measured on B200, profiles/r02*_small_lattices.md: from the 256^2 app
+    // default up to HPP 4096^2 = C2 and FHP-II 4096x2048 it beats the HBM-streaming wavefront kernel, by 1.1x at the
+    // top end and 5x on the reference's pipe).  LGCA_B200_FLAG_NO_RESIDENT / FORCE_RESIDENT: A-B tests.
     const bool hpp = rule_of(h->cfg.model) == MODEL_HPP;
     const int  nd = h->nd, nm = (hpp ? 0 : 1) + (h->has_ns ? 1 : 0) + (h->has_sl ? 1 : 0);
     const int  unit = hpp ? 1 : 2;
     const int  rows = (int)g.rows, sms = h->sm_count > 0 ? h->sm_count : 148;
     if (rows % unit) return p;
-    // steps per ghost-row exchange: cfg.k_fuse when given, else the deepest interval whose buffers fit (fewer
-    // exchanges, at the price of more redundant ghost-row work)
-    for (int K = h->cfg.k_fuse > 0 ? h->cfg.k_fuse : 8; K >= 1; --K) {
+    // Steps per ghost-row exchange K (H = K ghost rows per side, even for the hexagonal models): cfg.k_fuse when given,
+    // else the K in {8, 6, 4, 3, 2, 1} with the lowest modelled time per step: the slowest CTA computes r_max + K - 1 rows
+    // per step on average (trapezoid) and an exchange costs about 6000 cycles whatever its size (fitted to sweeps over K
+    // on C1 / pipe / HPP lattices: 3.2 us per exchange, 2.8 (FHP) / 1.2 (HPP) cycles per word and step).
+    ResPlan best;
+    memset(&best, 0, sizeof(best));
+    double best_cost = 1e300;
+    static const int ks[] = {8, 6, 4, 3, 2, 1};
+    for (int ki = 0; ki < 6; ++ki) {
+        const int K = h->cfg.k_fuse > 0 ? h->cfg.k_fuse : ks[ki];
+        if (K > 8) break;
         const int H = hpp ? K : ((K + 1) & ~1);
         const int units = rows / unit;
         int G = std::min(sms, units / std::max(1, (H + unit - 1) / unit)); // every strip at least H rows high
-        if (G < 1) continue;
-        const int base = units / G, extra = units % G;
-        const int r_max = (base + (extra ? 1 : 0)) * unit, r_min = base * unit;
-        if (r_min < H) continue;
-        const size_t smem = (size_t)(2 * nd + nm) * (size_t)(r_max + 2 * H) * g.pitch * sizeof(uint32_t);
-        if (smem > (size_t)RES_MAX_SMEM - 1024) continue;
-        p.ok = 1; p.G = G; p.unit = unit; p.base_units = base; p.extra_units = extra; p.H = H; p.K = K;
-        p.rows_max = r_max + 2 * H;
-        p.smem_bytes = smem;
-        p.exch_words = (size_t)2 * G * 2 * nd * H * g.pitch * 2; // {word, tag} messages
-        // thread mapping: static ownership while a thread owns at most 8 words of the CTA's local rows, else dynamic groups
-        const size_t words = (size_t)p.rows_max * g.nw;
-        const int    per_thread = (int)((words + 1023) / 1024);
-        p.own = per_thread <= 1 ? 1 : (per_thread <= 2 ? 2 : (per_thread <= 4 ? 4 : (per_thread <= 8 ? 8 : 0)));
-        if (h->cfg.flags & LGCA_B200_FLAG_RESIDENT_DYNAMIC) p.own = 0;
-        return p;
+        if (G >= 1) {
+            const int base = units / G, extra = units % G;
+            const int r_max = (base + (extra ? 1 : 0)) * unit, r_min = base * unit;
+            const size_t smem = (size_t)(2 * nd + nm) * (size_t)(r_max + 2 * H) * g.pitch * sizeof(uint32_t);
+            if (r_min >= H && smem <= (size_t)RES_MAX_SMEM - 1024) {
+                const double cost = (double)(r_max + K - 1) * g.nw * (hpp ? 1.2 : 2.8) + 6000.0 / K;
+                if (cost < best_cost) {
+                    best_cost = cost;
+                    ResPlan& q = best;
+                    q.ok = 1; q.G = G; q.unit = unit; q.base_units = base; q.extra_units = extra; q.H = H; q.K = K;
+                    q.rows_max = r_max + 2 * H;
+                    q.smem_bytes = smem;
+                    q.exch_words = (size_t)2 * G * 2 * nd * H * g.pitch * 2; // {word, tag} messages
+                    // thread mapping: static ownership while a thread owns at most 2 words of the CTA's local rows (beyond,
+                    // the register-resident per-word state spills and the LDS.128 groups win), else dynamic groups
+                    const size_t words = (size_t)q.rows_max * g.nw;
+                    q.own = words <= 1024 ? 1 : (words <= 2048 ? 2 : 0);
+                    if (h->cfg.flags & LGCA_B200_FLAG_RESIDENT_DYNAMIC) q.own = 0;
+                }
+            }
+        }
+        if (h->cfg.k_fuse > 0) break;
     }
-    return p;
+    if (!best.ok && h->cfg.k_fuse > 0) {
+        // the requested depth does not fit: fall back to shallower ones
+        for (int K = std::min(h->cfg.k_fuse, 8) - 1; K >= 1 && !best.ok; --K) {
+            lgca_b200_lattice tmp = *h;
+            tmp.cfg.k_fuse = K;
+            best = res_plan(&tmp);
+        }
+    }
+    return best;
 }
 
 bool resident_supported(const lgca_b200_lattice* h) { return res_plan(h).ok != 0; }
@@ -548,15 +575,11 @@ static int launch_res_variant(lgca_b200_lattice* h, const ResPlan& p, ResArgs& A
         int rc = RES_GO(0);
         if (!rc) rc = RES_GO(1);
         if (!rc) rc = RES_GO(2);
-        if (!rc) rc = RES_GO(4);
-        if (!rc) rc = RES_GO(8);
         return rc;
     }
     switch (p.own) {
     case 1: return RES_GO(1);
     case 2: return RES_GO(2);
-    case 4: return RES_GO(4);
-    case 8: return RES_GO(8);
     default: return RES_GO(0);
     }
 #undef RES_GO

@@ -292,14 +292,8 @@ __device__ __forceinline__ void tile_rows(const Geom& g, const WavePlan& wp, int
 {
     const int owned = (int)(g.rows - 2 * g.halo);
     if (wp.edge_rows == 0) {
-        const int big = wp.chunks - wp.tail_chunks;
-        if (c < big) {
-            oa = c * wp.chunk_rows;
-            ob = min(oa + wp.chunk_rows, owned);
-        } else {
-            oa = big * wp.chunk_rows + (c - big) * wp.tail_rows;
-            ob = min(oa + wp.tail_rows, owned);
-        }
+        oa = c * wp.chunk_rows;
+        ob = min(oa + wp.chunk_rows, owned);
     } else if (c == 0) {
         oa = 0; ob = wp.edge_rows;
     } else if (c == 1) {
@@ -498,28 +492,6 @@ static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
     wp.chunk_rows = cr;
     wp.edge_rows = 0;
     wp.chunks = (rows + cr - 1) / cr;
-    wp.tail_chunks = 0;
-    wp.tail_rows = 0;
-    {
-        // Tail filling (whole lattices whose plan is a single round): `tail_pct` percent of the rows go into short chunks
-        // of `tail_rows` rows at the end of the grid.  LGCA_B200_TAIL="pct,rows" overrides (sweeps).
-        const char* e_tail = getenv("LGCA_B200_TAIL");
-        int tail_pct = 0, tail_rows = 0;
-        if (e_tail) sscanf(e_tail, "%d,%d", &tail_pct, &tail_rows);
-        tail_rows = (tail_rows + 1) & ~1;
-        if (!g.halo && tail_pct > 0 && tail_rows >= 2 * k && tail_rows < cr) {
-            int n_tail = (int)((long long)rows * tail_pct / 100 / tail_rows);
-            int big_rows = rows - n_tail * tail_rows;
-            int n_big = big_rows / cr;                 // full chunks; the remainder joins the tail
-            const int rest = big_rows - n_big * cr;
-            n_tail += (rest + tail_rows - 1) / tail_rows;
-            if (n_big >= 1 && n_tail >= 1) {
-                wp.tail_chunks = n_tail;
-                wp.tail_rows = tail_rows;
-                wp.chunks = n_big + n_tail;
-            }
-        }
-    }
     if (g.halo) {
         // strips: two edge chunks of about 2/3 of an interior chunk (>= the rows the neighbours need and >= K + halo
         // so that no interior chunk reads ghost rows), interior chunks in between
