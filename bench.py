@@ -474,6 +474,29 @@ def run_b200_arm(args):
         e2e_s = float(t.item())
     e2e_value = sites_total * UPDATES_PER_STEP * e2e_steps / e2e_s
     coarse_bytes = sum(v.nbytes for v in coarse.values())
+    # what the box's host links deliver when all ranks copy at once (plain cudaMemcpy of the same pinned buffer, no
+    # pack/unpack kernels): the ceiling of the e2e figure above
+    link_probe = {}
+    try:
+        src = torch.from_numpy(host_state.array)
+        dev = torch.empty(sites_rank, dtype=torch.uint8, device=device)
+        for name, a, b in (("h2d", dev, src), ("d2h", src, dev)):
+            barrier()
+            torch.cuda.synchronize()
+            tp = time.perf_counter()
+            a.copy_(b, non_blocking=True)
+            torch.cuda.synchronize()
+            gbs = sites_rank / (time.perf_counter() - tp) / 1e9
+            if world > 1:
+                t = torch.tensor([gbs, -gbs], device=device, dtype=torch.float64)
+                dist.all_reduce(t, op=dist.ReduceOp.MIN)
+                link_probe[name + "_gbs_per_rank_min_max"] = [float(t[0].item()), float(-t[1].item())]
+            else:
+                link_probe[name + "_gbs_per_rank_min_max"] = [gbs, gbs]
+        link_probe["note"] = "all %d ranks copy %d MiB at once between pinned host memory and HBM (cudaMemcpyAsync)" % (world, sites_rank >> 20)
+        del dev
+    except Exception as ex:
+        link_probe = {"error": repr(ex)}
     host_state.free()
 
     # ---- mass conservation over the whole job (global particle count) ---------------------------------------
@@ -524,7 +547,7 @@ def run_b200_arm(args):
             "roofline": roofline,
             "e2e": {"value": e2e_value, "unit": "site updates/s", "h2d_bytes_per_step": sites_rank * world,
                     "d2h_bytes_per_step": (sites_rank + coarse_bytes) * world, "steps": e2e_steps,
-                    "h2d_gbs_per_rank_min_max": h2d_range,
+                    "h2d_gbs_per_rank_min_max": h2d_range, "host_link_probe": link_probe,
                     "path": "upload(pinned state bytes) -> [strips: stream-ordered republish of the ghost rows, no barrier] -> "
                             "100 steps -> snapshot+post_process -> download"},
             "gpu_launches": launches,

@@ -117,6 +117,7 @@ int run(const Args& a)
     opt.k_fuse = a.k_fuse;
     opt.cell_fields = a.cell_fields;
     opt.lazy_cell_fields = true; // the per-cell fields cross PCIe only when a writer needs them
+    opt.prefetch_draws = true;   // nothing else in this process calls rand() during the tick loop
     // --quiet: the base-class ctor prints the parameter banner; silence fd 1 around the construction only
     int saved_fd = -1;
     if (a.quiet) {

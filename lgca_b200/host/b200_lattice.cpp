@@ -52,6 +52,7 @@ B200_Lattice<model_>::B200_Lattice(const string test_case, unsigned int dim_x, u
 template <Model model_>
 B200_Lattice<model_>::~B200_Lattice()
 {
+    join_prefetch();
     if (m_h) lgca_b200_group_destroy(m_h);
     free_memory();
 }
@@ -204,6 +205,14 @@ std::vector<Real> B200_Lattice<model_>::get_mean_velocity()
 {
     std::vector<Real> mean_velocity(this->SPATIAL_DIM, 0.0);
     ensure_on_device();
+    join_prefetch();
+    if (m_opt.prefetch_draws && m_last_consumed) {
+        // the tick's next call is apply_body_force(): draw what it is expected to consume while the GPU and the walk
+        // below are busy (same FIFO, same order; joined before the FIFO is read)
+        const size_t target = m_last_consumed + m_last_consumed / 4;
+        if (draws_pending() < target)
+            m_prefetch = std::thread([this, target] { while (draws_pending() < target) m_draws.push_back(std::rand()); });
+    }
     float out[2];
     if (this->m_num_cells / (size_t)m_opt.n_gpus <= ((size_t)1 << 28)) {
         // the reference's loop at one thread (src/omp_lattice.cpp:508-557): sequential float32 sums over the cells of
@@ -228,6 +237,7 @@ template <Model model_>
 void B200_Lattice<model_>::apply_body_force(const int forcing)
 {
     ensure_on_device();
+    join_prefetch();
     // The reference draws `rand() % num_cells` one at a time until `forcing` particles are reverted or
     // 2*num_cells draws are spent (do-while: at least one draw; src/omp_lattice.cpp:254-346).  Here rand() values
     // are drawn ahead into a FIFO, handed to the device in order, and the unconsumed ones are kept for the next
@@ -236,17 +246,19 @@ void B200_Lattice<model_>::apply_body_force(const int forcing)
     size_t it = 0;
     long   remaining = (long)(unsigned int)forcing; // `unsigned int < int` compares as unsigned in the reference
     bool   first = true;
-    std::vector<int32_t> batch;
+    if (m_draw_head > (1u << 20) && m_draw_head * 2 > m_draws.size()) { // drop the consumed prefix now and then
+        m_draws.erase(m_draws.begin(), m_draws.begin() + m_draw_head);
+        m_draw_head = 0;
+    }
     while ((first || remaining > 0) && it < it_max) {
         size_t want = (size_t)std::max<double>(256.0, (double)std::max<long>(remaining, 1) * m_draws_per_hit * 1.25);
         want = std::min(want, it_max - it);
-        while (m_draws.size() < want) m_draws.push_back(std::rand());
-        batch.assign(m_draws.begin(), m_draws.begin() + want);
+        while (draws_pending() < want) m_draws.push_back(std::rand());
         size_t consumed = 0;
         uint32_t reverted = 0;
-        const int rc = lgca_b200_group_body_force(m_h, (int)remaining, batch.data(), want, &consumed, &reverted);
+        const int rc = lgca_b200_group_body_force(m_h, (int)remaining, m_draws.data() + m_draw_head, want, &consumed, &reverted);
         if (rc) fail("apply_body_force", rc);
-        m_draws.erase(m_draws.begin(), m_draws.begin() + consumed);
+        m_draw_head += consumed;
         it += consumed;
         remaining -= reverted;
         if (reverted > 0) m_draws_per_hit = 0.5 * m_draws_per_hit + 0.5 * std::min(1.0e4, (double)consumed / reverted);
@@ -254,6 +266,7 @@ void B200_Lattice<model_>::apply_body_force(const int forcing)
         first = false;
         if (consumed == 0) break;
     }
+    m_last_consumed = it;
 }
 
 template <Model model_>

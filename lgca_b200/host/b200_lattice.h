@@ -16,7 +16,7 @@
 #ifndef LGCA_B200_HOST_B200_LATTICE_H_
 #define LGCA_B200_HOST_B200_LATTICE_H_
 
-#include <deque>
+#include <thread>
 
 #include "lattice.h"
 
@@ -35,6 +35,10 @@ struct B200Options {
     bool lazy_cell_fields = false; // post_process() leaves the per-cell host fields alone (12 B/cell over PCIe per call);
                                    // sync_cell_fields() computes them from the same output buffer when a writer asks
     bool exact_post  = true;  // reference summation order for the coarse momentum-y means
+    bool prefetch_draws = false; // get_mean_velocity() starts a helper thread that draws the rand() values the following
+                                 // apply_body_force() is expected to consume (glibc rand(): 6-20 ns per draw, ~8 draws per
+                                 // reverted particle) while the mean velocity is computed.  The draws enter the same FIFO in
+                                 // the same order; only for callers whose other threads do not call rand() meanwhile.
 };
 
 template <Model model_>
@@ -75,7 +79,12 @@ private:
     lgca_b200_group*   m_h = nullptr;     // one lattice on n_gpus devices (n_gpus == 1: a plain whole-lattice handle)
     bool               m_on_device = false;   // host mirrors have been uploaded
     bool               m_cell_fields_stale = false; // lazy mode: the last post_process() skipped the per-cell fields
-    std::deque<int>    m_draws;               // rand() values drawn ahead for the body force, in stream order
+    std::vector<int32_t> m_draws;             // rand() values drawn ahead for the body force, in stream order;
+    size_t             m_draw_head = 0;       // the unconsumed ones are m_draws[m_draw_head ..]
+    size_t             draws_pending() const { return m_draws.size() - m_draw_head; }
+    std::thread        m_prefetch;            // helper drawing ahead into m_draws (prefetch_draws)
+    size_t             m_last_consumed = 0;   // draws the last apply_body_force() consumed
+    void               join_prefetch() { if (m_prefetch.joinable()) m_prefetch.join(); }
     double             m_draws_per_hit = 8.0; // running estimate used to size the draw-ahead
 };
 
