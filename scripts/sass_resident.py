@@ -22,6 +22,6 @@ for line in sass.splitlines():
 print("# SASS evidence: SM-resident kernel (csrc/lgca_step_resident.cu), `cuobjdump -sass lgca_b200/liblgca_b200.so` (sm_100a)\n")
 print("`UBLKCP.S.G` = TMA-family bulk copy global -> shared (staging the lattice once per call), `UBLKCP.G.S` = shared -> global")
 print("(write-back after the last step), `SYNCS.*TRANS64` = mbarrier transaction waits of those copies, `LDS.128/STS.128` = the")
-print("four-words-per-thread row accesses.  Template arguments: <MODEL, HAS_NO_SLIP, HAS_SLIP>.\n")
+print("four-words-per-thread row accesses.  Template arguments: <MODEL, HAS_NO_SLIP, HAS_SLIP, OWN> (OWN = words a thread owns statically, 0 = dynamic four-word groups).\n")
 for fn, c in counts.items():
     print("* `%s`: " % fn + ", ".join("%s x%d" % kv for kv in sorted(c.items())))
