@@ -513,13 +513,20 @@ def run_b200_arm(args):
     e.sync()
     e.timed_kernel(5)
     kms = min(e.timed_kernel(25) for _ in range(3))
+    # the ring couples the ranks (every block waits for both neighbours' ghost rows), so the job runs at the pace of the
+    # slowest GPU: the spread of the stand-alone kernel time over the ranks shows how much of the N-GPU loss is silicon
+    kms_range = [kms, kms]
+    if world > 1:
+        t = torch.tensor([kms, -kms], device=device, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        kms_range = [float(t[0].item()), float(-t[1].item())]
     alg_bytes = sites_rank * info.bytes_per_site_step_x8 / 8.0 * k
     peak, peak_src = measured_peak()
     achieved = alg_bytes / (kms * 1e-3) / 1e9
     traffic, traffic_note = measured_traffic("%s_k%d" % (args.workload, k))
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "frac_of_nominal_8TBs": achieved / 8000.0, "traffic": traffic, "traffic_source": traffic_note, "kernel": "step_wave_kernel<FHP_II rule, K=%d>" % k,
-                "launch_ms": kms, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
+                "launch_ms": kms, "launch_ms_rank_min_max": kms_range, "alg_bytes_per_launch": alg_bytes, "peak_source": peak_src,
                 "dram_frac": (traffic / (kms * 1e-3) / 1e9 / peak) if traffic else None,
                 "limiter": "integer pipe + issue slots (LOP3/SHF/SHFL; sm__pipe_alu and issue_active in profiles/), not DRAM: dram_frac is the share of the copy peak the kernel really moves",
                 "note": "algorithmic bytes = sites*(2*NUM_DIR+masks)/8 per step x k fused steps per launch; "

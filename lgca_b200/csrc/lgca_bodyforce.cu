@@ -180,7 +180,8 @@ static int ensure_bf_buffers(lgca_b200_lattice* h, size_t n)
 
 void free_bf_buffers(lgca_b200_lattice* h)
 {
-    cudaFree(h->d_bf_draws); cudaFree(h->d_bf_keys); cudaFree(h->d_bf_gain); cudaFree(h->d_bf_blocks);
+    cudaFree(h->d_bf_draws); cudaFree(h->d_bf_keys); cudaFree(h->d_bf_gain); cudaFree(h->d_bf_blocks); cudaFree(h->d_bf_peer);
+    if (h->ev_bf) cudaEventDestroy(h->ev_bf);
 }
 
 // One batch on a whole-lattice handle.  `first`: the batch opens a body-force call (the do-while's unconditional first
@@ -228,6 +229,177 @@ int body_force_device(lgca_b200_lattice* h, uint32_t forcing, bool first, const 
     LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
     *consumed = host2[0];
     *reverted = host2[1];
+    return 0;
+}
+
+// ---- the same semantics over ROW STRIPS (lgca_group.cu) ---------------------------------------------------------------
+// Every strip classifies the whole batch against its own rows (first occurrences are a property of the draw sequence, so
+// every strip builds the same hash table; gains are non-zero on the owner only), the gains are summed on the first strip's
+// device (peer copies), which runs the prefix sum and the stop rule; every strip then scatters its own reverts up to the cut.
+
+__global__ void __launch_bounds__(BF_BLOCK) bf_combine_kernel(uint8_t* __restrict__ gain, const uint8_t* __restrict__ other, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * BF_BLOCK + threadIdx.x;
+    if (i < n) gain[i] = (uint8_t)(gain[i] | other[i]); // at most one strip owns the cell
+}
+
+__global__ void __launch_bounds__(BF_BLOCK) bf_block_sums_kernel(const uint8_t* __restrict__ gain, uint32_t n, uint32_t* __restrict__ block_sums)
+{
+    const uint32_t i = blockIdx.x * BF_BLOCK + threadIdx.x;
+    uint32_t s = i < n ? gain[i] : 0u;
+    __shared__ uint32_t sh[BF_BLOCK / 32];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xFFFFFFFFu, s, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int w = 0; w < BF_BLOCK / 32; ++w) t += sh[w];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// the stop rule alone: out2 = { consumed, reverted }
+__global__ void __launch_bounds__(BF_BLOCK) bf_cutoff_kernel(const uint8_t* __restrict__ gain, uint32_t n, const uint32_t* __restrict__ block_offsets,
+                                                             uint32_t forcing, uint32_t first, uint32_t* __restrict__ out2)
+{
+    const uint32_t i = blockIdx.x * BF_BLOCK + threadIdx.x;
+    const uint32_t gn = i < n ? gain[i] : 0u;
+    __shared__ uint32_t sh[BF_BLOCK / 32];
+    uint32_t s = gn;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, s, o); if ((threadIdx.x & 31) >= o) s += t; }
+    if ((threadIdx.x & 31) == 31) sh[threadIdx.x >> 5] = s;
+    __syncthreads();
+    uint32_t off = block_offsets[blockIdx.x];
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) off += sh[w];
+    if (i >= n) return;
+    const uint32_t incl = off + s, excl = incl - gn;
+    if (!((i == 0 && first) || excl < forcing)) return;
+    if (i == n - 1 || !(incl < forcing)) { out2[0] = i + 1; out2[1] = incl; }
+}
+
+// scatter of the strip's own reverts among the first `consumed` draws
+template <int ND>
+__global__ void __launch_bounds__(BF_BLOCK) bf_apply_cut_kernel(uint32_t* __restrict__ planes, const int32_t* __restrict__ draws, uint32_t consumed,
+                                                                uint32_t num_cells, const uint8_t* __restrict__ gain, const Geom g,
+                                                                uint32_t own_rows, int bf)
+{
+    const uint32_t i = blockIdx.x * BF_BLOCK + threadIdx.x;
+    if (i >= consumed || !gain[i]) return;
+    const uint32_t cell = (uint32_t)draws[i] % num_cells;
+    const uint32_t gy = cell / g.dim_x, x = cell % g.dim_x;
+    if (gy < g.y0 || gy >= g.y0 + own_rows) return; // another strip's cell (the first strip holds the combined gains)
+    const size_t   base = (size_t)(gy - g.y0 + g.halo) * g.pitch + (x >> 5);
+    const uint32_t m = 1u << (x & 31);
+    auto move = [&](int from, int to) {
+        atomicAnd(planes + (size_t)from * g.plane_stride + base, ~m);
+        atomicOr(planes + (size_t)to * g.plane_stride + base, m);
+    };
+    if (ND == 4) {
+        if (bf == 'x') move(2, 0); else move(1, 3);
+    } else if (bf == 'x') {
+        move(3, 0);
+    } else {
+        const uint32_t b1 = (planes[(size_t)1 * g.plane_stride + base] & m) && !(planes[(size_t)5 * g.plane_stride + base] & m);
+        const uint32_t b2 = (planes[(size_t)2 * g.plane_stride + base] & m) && !(planes[(size_t)4 * g.plane_stride + base] & m);
+        if (b1) move(1, 5);
+        if (b2) move(2, 4);
+    }
+}
+
+// stage 1 on one strip: draws -> device, hash table, gains of the strip's own cells (asynchronous; ev_bf marks the end)
+int body_force_classify(lgca_b200_lattice* h, const int32_t* draws, size_t n)
+{
+    const Geom& g = h->g;
+    const uint32_t num_cells = (uint32_t)((uint64_t)g.dim_x * g.dim_y);
+    LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+    int rc = ensure_bf_buffers(h, n);
+    if (rc) return rc;
+    if (!h->ev_bf) LGCA_CUDA_CHECK(cudaEventCreateWithFlags(&h->ev_bf, cudaEventDisableTiming));
+    cudaStream_t s = h->s_compute;
+    size_t slots = 1 << 10;
+    while (slots < 2 * n) slots <<= 1;
+    uint32_t* keys = h->d_bf_keys;
+    uint32_t* vals = h->d_bf_keys + slots;
+    const uint32_t nb = (uint32_t)((n + BF_BLOCK - 1) / BF_BLOCK);
+    const int bf = h->cfg.bf_dir;
+    LGCA_CUDA_CHECK(cudaMemcpyAsync(h->d_bf_draws, draws, n * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    LGCA_CUDA_CHECK(cudaMemsetAsync(keys, 0xFF, 2 * slots * sizeof(uint32_t), s));
+    const uint32_t* planes = h->planes[h->cur];
+    const uint32_t own = g.rows - 2 * g.halo;
+    bf_insert_kernel<<<nb, BF_BLOCK, 0, s>>>(h->d_bf_draws, (uint32_t)n, num_cells, keys, vals, (uint32_t)slots - 1);
+#define BF_CLASSIFY(ND) bf_classify_kernel<ND><<<nb, BF_BLOCK, 0, s>>>(planes, h->ns, h->sl, h->d_bf_draws, (uint32_t)n, num_cells, keys, vals, \
+                                                                       (uint32_t)slots - 1, h->d_bf_gain, h->d_bf_blocks, g, own, bf)
+    if (h->nd == 4) BF_CLASSIFY(4); else if (h->nd == 6) BF_CLASSIFY(6); else BF_CLASSIFY(7);
+#undef BF_CLASSIFY
+    h->launches += 2;
+    LGCA_CUDA_CHECK(cudaGetLastError());
+    LGCA_CUDA_CHECK(cudaEventRecord(h->ev_bf, s));
+    return 0;
+}
+
+// stage 2 on the first strip: add another strip's gains (peer copy ordered behind that strip's classification)
+int body_force_combine(lgca_b200_lattice* h0, lgca_b200_lattice* other, size_t n)
+{
+    LGCA_CUDA_CHECK(cudaSetDevice(h0->cfg.device));
+    if (h0->bf_peer_cap < n) {
+        cudaFree(h0->d_bf_peer);
+        h0->d_bf_peer = nullptr; h0->bf_peer_cap = 0;
+        LGCA_CUDA_CHECK(cudaMalloc((void**)&h0->d_bf_peer, h0->bf_cap));
+        h0->bf_peer_cap = h0->bf_cap;
+    }
+    cudaStream_t s = h0->s_compute;
+    LGCA_CUDA_CHECK(cudaStreamWaitEvent(s, other->ev_bf, 0));
+    LGCA_CUDA_CHECK(cudaMemcpyPeerAsync(h0->d_bf_peer, h0->cfg.device, other->d_bf_gain, other->cfg.device, n, s));
+    bf_combine_kernel<<<(unsigned)((n + BF_BLOCK - 1) / BF_BLOCK), BF_BLOCK, 0, s>>>(h0->d_bf_gain, h0->d_bf_peer, (uint32_t)n);
+    h0->launches++;
+    LGCA_CUDA_CHECK(cudaGetLastError());
+    return 0;
+}
+
+// stage 3 on the first strip: prefix sum + stop rule over the combined gains (synchronous)
+int body_force_cutoff(lgca_b200_lattice* h0, uint32_t forcing, bool first, size_t n, size_t* consumed, uint32_t* reverted)
+{
+    LGCA_CUDA_CHECK(cudaSetDevice(h0->cfg.device));
+    cudaStream_t s = h0->s_compute;
+    const uint32_t nb = (uint32_t)((n + BF_BLOCK - 1) / BF_BLOCK);
+    uint32_t* out2 = reinterpret_cast<uint32_t*>(h0->d_scalars + 6);
+    LGCA_CUDA_CHECK(cudaMemsetAsync(out2, 0, 2 * sizeof(uint32_t), s));
+    bf_block_sums_kernel<<<nb, BF_BLOCK, 0, s>>>(h0->d_bf_gain, (uint32_t)n, h0->d_bf_blocks);
+    bf_scan_blocks_kernel<<<1, 1024, 0, s>>>(h0->d_bf_blocks, nb);
+    bf_cutoff_kernel<<<nb, BF_BLOCK, 0, s>>>(h0->d_bf_gain, (uint32_t)n, h0->d_bf_blocks, forcing, first ? 1u : 0u, out2);
+    h0->launches += 3;
+    LGCA_CUDA_CHECK(cudaGetLastError());
+    uint32_t* host2 = reinterpret_cast<uint32_t*>(h0->h_scalars + 6);
+    LGCA_CUDA_CHECK(cudaMemcpyAsync(host2, out2, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    LGCA_CUDA_CHECK(cudaStreamSynchronize(s));
+    *consumed = host2[0];
+    *reverted = host2[1];
+    return 0;
+}
+
+// stage 4 on every strip: scatter (asynchronous on the strip's compute stream)
+int body_force_apply_cut(lgca_b200_lattice* h, size_t n, size_t consumed)
+{
+    (void)n;
+    if (consumed == 0) return 0;
+    LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
+    int rc;
+    if ((rc = unalias_snapshot(h))) return rc; // in-place write: the snapshot must not see it
+    if ((rc = ring_order_inplace_write(h))) return rc;
+    const Geom& g = h->g;
+    const uint32_t num_cells = (uint32_t)((uint64_t)g.dim_x * g.dim_y);
+    const uint32_t own = g.rows - 2 * g.halo;
+    const uint32_t nb = (uint32_t)((consumed + BF_BLOCK - 1) / BF_BLOCK);
+    uint32_t* planes = h->planes[h->cur];
+    const int bf = h->cfg.bf_dir;
+    cudaStream_t s = h->s_compute;
+#define BF_CUT(ND) bf_apply_cut_kernel<ND><<<nb, BF_BLOCK, 0, s>>>(planes, h->d_bf_draws, (uint32_t)consumed, num_cells, h->d_bf_gain, g, own, bf)
+    if (h->nd == 4) BF_CUT(4); else if (h->nd == 6) BF_CUT(6); else BF_CUT(7);
+#undef BF_CUT
+    h->launches++;
+    LGCA_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 

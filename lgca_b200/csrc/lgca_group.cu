@@ -317,6 +317,35 @@ int lgca_b200_group_body_force(lgca_b200_group* g, int forcing, const int32_t* d
     size_t pos = 0;
     int64_t remaining = (int64_t)(uint32_t)forcing;
     bool first = true, changed = false;
+    if (!(g->cfg.flags & LGCA_B200_FLAG_HOST_BODY_FORCE)) {
+        // device path: classification on every strip, gains summed on the first strip (peer copies), prefix sum + stop rule
+        // there, scatter of the own reverts on every strip (csrc/lgca_bodyforce.cu)
+        lgca_b200_lattice* h0 = g->strips[0];
+        while (pos < n_draws && (first || remaining > 0)) {
+            const size_t batch = std::min<size_t>(n_draws - pos, (size_t)1 << 22);
+            for (lgca_b200_lattice* h : g->strips)
+                if ((rc = body_force_classify(h, draws + pos, batch))) return rc;
+            for (size_t i = 1; i < n_strips(g); ++i)
+                if ((rc = body_force_combine(h0, g->strips[i], batch))) return rc;
+            size_t used = 0;
+            uint32_t rev = 0;
+            if ((rc = body_force_cutoff(h0, (uint32_t)remaining, first, batch, &used, &rev))) return rc;
+            if (rev) {
+                // every strip gets the call: the copy-on-write of the snapshot must happen on all strips or on none
+                for (lgca_b200_lattice* h : g->strips)
+                    if ((rc = body_force_apply_cut(h, batch, used))) return rc;
+                changed = true;
+            }
+            pos += used;
+            remaining -= rev;
+            *reverted += rev;
+            first = false;
+            if (used < batch) break;
+        }
+        *consumed = pos;
+        if (changed) { g->published = false; if ((rc = publish(g))) return rc; }
+        return 0;
+    }
     while (pos < n_draws && (first || remaining > 0)) {
         size_t batch = (size_t)std::max<int64_t>(4096, std::min<int64_t>(1 << 20, remaining * 12));
         batch = std::min(batch, n_draws - pos);

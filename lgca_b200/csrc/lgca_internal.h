@@ -104,6 +104,9 @@ struct lgca_b200_lattice {
     uint8_t*         d_bf_gain;
     uint32_t*        d_bf_blocks;
     size_t           bf_cap;
+    uint8_t*         d_bf_peer;             // first strip of a group: another strip's gains (peer copy)
+    size_t           bf_peer_cap;
+    cudaEvent_t      ev_bf;                 // end of this strip's classification
     // order-exact mean velocity (lgca_mv.cu): rounding tables, per-segment summaries, class bytes + pinned mirrors
     int32_t*         d_mv_tab;
     int32_t*         d_mv_rec;
@@ -146,6 +149,11 @@ void free_mv_buffers(lgca_b200_lattice* h); // lgca_mv.cu
 void free_bf_buffers(lgca_b200_lattice* h); // lgca_bodyforce.cu
 int body_force_device(lgca_b200_lattice* h, uint32_t forcing, bool first, const int32_t* draws, size_t n, size_t* consumed,
                       uint32_t* reverted); // lgca_bodyforce.cu: one batch, whole-lattice handles
+// ... and its four stages over row strips (lgca_group.cu drives them)
+int body_force_classify(lgca_b200_lattice* h, const int32_t* draws, size_t n);
+int body_force_combine(lgca_b200_lattice* h0, lgca_b200_lattice* other, size_t n);
+int body_force_cutoff(lgca_b200_lattice* h0, uint32_t forcing, bool first, size_t n, size_t* consumed, uint32_t* reverted);
+int body_force_apply_cut(lgca_b200_lattice* h, size_t n, size_t consumed);
 int steps_per_launch(const lgca_b200_lattice* h, int want); // lgca_capi.cu: steps ONE kernel launch can advance (<= want)
 inline int buffer_id(const lgca_b200_lattice* h, const uint32_t* p)
 {

@@ -47,13 +47,16 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("host_bf", [False, True], ids=["device-bf", "host-bf"])
 @pytest.mark.parametrize("devs", device_sets())
 @pytest.mark.parametrize("model,dims,bc,cg,k", CASES, ids=lambda c: str(c))
-def test_group_equals_oracle(model, dims, bc, cg, k, devs):
+def test_group_equals_oracle(model, dims, bc, cg, k, devs, host_bf):
     o = Oracle(model, dims=dims, cg=cg, bf_dir=b"x", rng=OracleRng(17))
     o.apply_bc(bc)
     o.init("random")
-    g = group_from(o, devs, k_fuse=k, cg=cg)
+    # body force: the device-side path (classification per strip, gains summed over peer copies, prefix + stop rule, scatter)
+    # and the gather -> ordered host replay -> apply path (flag 16) must both reproduce the reference's sequential loop
+    g = group_from(o, devs, k_fuse=k, cg=cg, flags=16 if host_bf else 0)
     assert np.array_equal(g.download(), o.state)
     assert g.count_particles() == o.n_particles()
     o.rng = OracleRng(5)
@@ -68,6 +71,7 @@ def test_group_equals_oracle(model, dims, bc, cg, k, devs):
         for name in ("cell_density", "cell_momentum", "mean_density", "mean_momentum"):
             assert np.array_equal(f[name], getattr(o, name)), (name, rounds)
         np.testing.assert_allclose(g.mean_velocity(), o.mean_velocity(), rtol=0, atol=1e-6)
+        assert g.mean_velocity_exact().tobytes() == np.asarray(o.mean_velocity(), np.float32).tobytes()  # the one-thread digits
         # body force on the live state right after the snapshot (the canonical schedule), then step on
         forcing = (0, 7, 120, 900)[rounds]
         used_o, rev_o = o.body_force(forcing)
