@@ -472,8 +472,15 @@ static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
     WavePlan wp;
     wp.bands = ((int)g.nw + WAVE_VALID - 1) / WAVE_VALID;
     const int rows = (int)(g.rows - 2 * g.halo); // owned rows
+    // tiling overrides for sweeps (scripts/chunk_sweep.py): results are identical for every tiling; only builds with
+    // -DLGCA_B200_TUNING read the environment
+#ifdef LGCA_B200_TUNING
     const char* e_cr = getenv("LGCA_B200_CHUNK_ROWS");
     const char* e_res = getenv("LGCA_B200_RESIDENT_WARPS");
+#else
+    const char* e_cr = nullptr;
+    const char* e_res = nullptr;
+#endif
     const double resident = e_res ? atof(e_res) : (double)resident_warps;
     int    best_cr = (rows + 1) & ~1;
     double best = 1e300;

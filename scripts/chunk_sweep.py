@@ -1,4 +1,5 @@
-"""Chunk-height sweep of the fused-step kernel (development helper): LGCA_B200_CHUNK_ROWS is read when the plan is made."""
+"""Chunk-height sweep of the fused-step kernel (development helper): LGCA_B200_CHUNK_ROWS is read when the plan is made --
+only by a tuning build: scripts/build_variant.sh ab_tuning.so -DLGCA_B200_TUNING; LGCA_B200_LIB=$PWD/ab_tuning.so python scripts/chunk_sweep.py"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import lgca_b200
