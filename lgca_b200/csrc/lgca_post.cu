@@ -126,6 +126,68 @@ __global__ void __launch_bounds__(128) mean_fields_kernel(const uint32_t* __rest
     if (mmom) { mmom[2 * cc] = __fdiv_rn(mx, cnt); mmom[2 * cc + 1] = __fdiv_rn(my, cnt); }
 }
 
+// ---- coarse-grained means, popcount BLOCK reduction (the non-exact mode) ---------------------------------------------
+// Block = 32 coarse cells of one coarse row x MF_SLICES row slices: a warp reads the same lattice row for 32 neighbouring
+// windows (consecutive words: coalesced), the slices split the 2r+1 window rows, the per-plane popcounts meet in shared
+// memory.  Same window, same integer sums, hence the same floats as mean_fields_kernel<ND, false>.
+constexpr int MF_SLICES = 8;
+template <int ND>
+__global__ void __launch_bounds__(32 * MF_SLICES) mean_fields_block_kernel(const uint32_t* __restrict__ planes,
+                                                                          const uint32_t* __restrict__ ghost_row,
+                                                                          float* __restrict__ mrho, float* __restrict__ mmom,
+                                                                          const Geom g, uint32_t cg, uint32_t coarse_dim_x,
+                                                                          uint32_t coarse_row0)
+{
+    __shared__ int s_pc[MF_SLICES][ND][32];
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint32_t cx = blockIdx.x * 32 + tx, cr = blockIdx.y, cy = coarse_row0 + cr;
+    const uint32_t ax = cx * 2u * cg, ay = cy * 2u * cg, x1 = ax + cg;
+    int pc[ND];
+#pragma unroll
+    for (int d = 0; d < ND; ++d) pc[d] = 0;
+    if (cx < coarse_dim_x) {
+        for (uint32_t dy = ty; dy <= 2u * cg; dy += MF_SLICES) {
+            const uint32_t gy = ay + dy;
+            if (gy >= g.dim_y) break;
+            const uint32_t sy = gy - g.y0 + g.halo;
+            const bool     beyond = ghost_row != nullptr && sy >= g.rows - g.halo;
+            const uint32_t* src = beyond ? ghost_row : planes;
+            const size_t pstride = beyond ? (size_t)g.pitch : (size_t)g.plane_stride;
+            const size_t rb = beyond ? 0 : (size_t)sy * g.pitch;
+            for (uint32_t w = ax >> 5; w <= (x1 >> 5); ++w) {
+                uint32_t m = 0xFFFFFFFFu;
+                if (w == (ax >> 5)) m &= 0xFFFFFFFFu << (ax & 31);
+                if (w == (x1 >> 5)) m &= low_mask((int)(x1 & 31) + 1);
+#pragma unroll
+                for (int d = 0; d < ND; ++d) pc[d] += __popc(__ldg(src + (size_t)d * pstride + rb + w) & m);
+            }
+        }
+    }
+#pragma unroll
+    for (int d = 0; d < ND; ++d) s_pc[ty][d][tx] = pc[d];
+    __syncthreads();
+    if (ty != 0 || cx >= coarse_dim_x) return;
+#pragma unroll
+    for (int d = 0; d < ND; ++d)
+        for (int sl = 1; sl < MF_SLICES; ++sl) pc[d] += s_pc[sl][d][tx];
+    const uint32_t rows_in = min(2u * cg + 1u, g.dim_y - ay); // window rows inside the global domain
+    const float cnt = (float)((int)rows_in * (int)(cg + 1));
+    int dsum = 0;
+#pragma unroll
+    for (int d = 0; d < ND; ++d) dsum += pc[d];
+    float mx, my;
+    if (ND == 4) {
+        mx = (float)(pc[0] - pc[2]);
+        my = (float)(pc[1] - pc[3]);
+    } else {
+        mx = __fmul_rn((float)(2 * (pc[0] - pc[3]) + pc[1] + pc[5] - pc[2] - pc[4]), 0.5f);
+        my = __fmul_rn((float)(pc[1] + pc[2] - pc[4] - pc[5]), LGCA_SIN_F);
+    }
+    const size_t cc = (size_t)cr * coarse_dim_x + cx;
+    if (mrho) mrho[cc] = __fdiv_rn((float)dsum, cnt);
+    if (mmom) { mmom[2 * cc] = __fdiv_rn(mx, cnt); mmom[2 * cc + 1] = __fdiv_rn(my, cnt); }
+}
+
 // ---- mean velocity (device reduction, double accumulation) -----------------------------------------
 // out3 = { sum_x, sum_y, #fluid cells } over the owned rows.
 template <int ND>
@@ -263,8 +325,15 @@ int launch_mean_fields(lgca_b200_lattice* h, const uint32_t* planes, const uint3
     if (cdx == 0 || crows == 0) return 0;
     dim3 grid((cdx + 127) / 128, crows, 1);
 #define MF(ND, EX) mean_fields_kernel<ND, EX><<<grid, 128, 0, s>>>(planes, ghost_row, d_mrho, d_mmom, g, cg, cdx, crows, crow0)
-    if (exact) DISPATCH_ND(h->nd, (MF(4, true)), (MF(6, true)), (MF(7, true)));
-    else       DISPATCH_ND(h->nd, (MF(4, false)), (MF(6, false)), (MF(7, false)));
+    if (exact) {
+        DISPATCH_ND(h->nd, (MF(4, true)), (MF(6, true)), (MF(7, true)));
+    } else {
+        // popcount block reduction (32 coarse cells x MF_SLICES row slices per block)
+        dim3 bgrid((cdx + 31) / 32, crows, 1);
+#define MFB(ND) mean_fields_block_kernel<ND><<<bgrid, 32 * MF_SLICES, 0, s>>>(planes, ghost_row, d_mrho, d_mmom, g, cg, cdx, crow0)
+        DISPATCH_ND(h->nd, (MFB(4)), (MFB(6)), (MFB(7)));
+#undef MFB
+    }
 #undef MF
     h->launches++;
     LGCA_CUDA_CHECK(cudaGetLastError());
