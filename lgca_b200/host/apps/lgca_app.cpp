@@ -34,7 +34,7 @@ struct Args {
     std::vector<int> devices;
     int         hash_every = 0;
     unsigned    dim_x = 0, dim_y = 0;
-    bool        cell_fields = true, quiet = false, bc_forward = false;
+    bool        cell_fields = true, quiet = false, bc_forward = false, plain_rand = false;
     std::string output = "none", out_dir = "./", scalars = "Mean momentum";
     int         zoom = 1;
 };
@@ -51,7 +51,7 @@ void usage(const char* argv0)
     printf("usage: %s [-r Re] [-m Ma] [-d 4|6|7] [--model HPP|FHP_I|FHP_II|FHP_III] [-s steps] [-c cg-radius]\n"
            "          [-w write-steps] [--pp-interval n] [--dims X Y] [--device n] [--gpus n | --devices a,b,..] [--k-fuse k]\n"
            "          [-o none|vti|png] [--out-dir d] [--scalars \"Mean momentum\"] [--zoom n]\n"
-           "          [--hash-every n] [--bounce forward|back] [--no-cell-fields] [--quiet]\n", argv0);
+           "          [--hash-every n] [--bounce forward|back] [--no-cell-fields] [--quiet] [--plain-rand]\n", argv0);
 }
 
 bool parse(int argc, char** argv, Args& a)
@@ -99,6 +99,7 @@ bool parse(int argc, char** argv, Args& a)
         else if (f == "--bounce") a.bc_forward = std::string(next("bounce")) == "forward";
         else if (f == "--no-cell-fields") a.cell_fields = false;
         else if (f == "--quiet") a.quiet = true;
+        else if (f == "--plain-rand") a.plain_rand = true;   // body-force draws through rand() calls only (A-B of bulk_rand)
         else if (f == "-p" || f == "--parallel") { std::string p = next("parallel"); if (p != "B200" && p != "CUDA") { printf("ERROR in main(): Invalid parallelization type %s (only B200).\n", p.c_str()); exit(2); } }
         else if (f == "--bf-steps" || f == "--bf-int" || f == "--blocksize") next(f.c_str()); // accepted, unused (as in the reference's live apps)
         else if (f == "-h" || f == "--help") { usage(argv[0]); exit(0); }
@@ -118,6 +119,7 @@ int run(const Args& a)
     opt.cell_fields = a.cell_fields;
     opt.lazy_cell_fields = true; // the per-cell fields cross PCIe only when a writer needs them
     opt.prefetch_draws = true;   // nothing else in this process calls rand() during the tick loop
+    opt.bulk_rand = !a.plain_rand;
     // --quiet: the base-class ctor prints the parameter banner; silence fd 1 around the construction only
     int saved_fd = -1;
     if (a.quiet) {

@@ -8,6 +8,66 @@
 
 namespace lgca {
 
+// ---- bulk rand() ----------------------------------------------------------------------------------------------------
+// glibc's rand() is random(): a lock, then one step of the TYPE_3 additive feedback generator on its default state table
+// (stdlib/random_r.c: `val = *fptr += *rptr; result = val >> 1`, degree 31, separation 3).  initstate() / setstate() are the
+// documented way to move that generator between state arrays: initstate(seed, mine, n) makes it use `mine` and returns
+// the OLD array, whose first word then holds 5 * rear_index + type.  While the generator is parked on the dummy array the
+// default table is advanced here by the same recurrence, the rear index is written back and setstate() returns the
+// generator to it: the stream continues exactly where bulk generation stopped.
+bool bulk_rand_fill(std::vector<int32_t>& out, size_t n)
+{
+    static char dummy[128];
+    char* old = initstate(1u, dummy, sizeof(dummy));
+    if (!old) return false;
+    int32_t* st = reinterpret_cast<int32_t*>(old);
+    const int type = st[0] % 5, rear0 = st[0] / 5;
+    bool ok = type == 3 && rear0 >= 0 && rear0 < 31;
+    if (ok) {
+        uint32_t* state = reinterpret_cast<uint32_t*>(st + 1);
+        int r = rear0, f = (rear0 + 3) % 31;
+        const size_t base = out.size();
+        out.resize(base + n);
+        int32_t* dst = out.data() + base;
+        for (size_t i = 0; i < n; ++i) {
+            const uint32_t val = state[f] += state[r];
+            dst[i] = (int32_t)(val >> 1);
+            if (++f == 31) f = 0;
+            if (++r == 31) r = 0;
+        }
+        st[0] = 5 * r + type;
+    }
+    setstate(old);
+    return ok;
+}
+
+// first use: the bulk generator must reproduce rand() itself -- 32 values computed on a COPY of the state are compared
+// with 32 real rand() calls (which are the next values of the stream and go into the FIFO like any other draw)
+bool bulk_rand_selfcheck(std::vector<int32_t>& out)
+{
+    static char dummy[128];
+    char* old = initstate(1u, dummy, sizeof(dummy));
+    if (!old) return false;
+    int32_t copy[32];
+    std::memcpy(copy, old, sizeof(copy));
+    setstate(old);
+    const int type = copy[0] % 5, rear0 = copy[0] / 5;
+    bool ok = type == 3 && rear0 >= 0 && rear0 < 31;
+    uint32_t* state = reinterpret_cast<uint32_t*>(copy + 1);
+    int r = rear0, f = (rear0 + 3) % 31;
+    for (int i = 0; i < 32; ++i) {
+        const int real = std::rand();
+        out.push_back(real);
+        if (ok) {
+            const uint32_t val = state[f] += state[r];
+            ok = (int32_t)(val >> 1) == real;
+            if (++f == 31) f = 0;
+            if (++r == 31) r = 0;
+        }
+    }
+    return ok;
+}
+
 namespace {
 void* pinned_alloc(size_t bytes)
 {
@@ -210,8 +270,7 @@ std::vector<Real> B200_Lattice<model_>::get_mean_velocity()
         // the tick's next call is apply_body_force(): draw what it is expected to consume while the GPU and the walk
         // below are busy (same FIFO, same order; joined before the FIFO is read)
         const size_t target = m_last_consumed + m_last_consumed / 4;
-        if (draws_pending() < target)
-            m_prefetch = std::thread([this, target] { while (draws_pending() < target) m_draws.push_back(std::rand()); });
+        if (draws_pending() < target) m_prefetch = std::thread([this, target] { draw_until(target); });
     }
     float out[2];
     if (this->m_num_cells / (size_t)m_opt.n_gpus <= ((size_t)1 << 28)) {
@@ -253,7 +312,7 @@ void B200_Lattice<model_>::apply_body_force(const int forcing)
     while ((first || remaining > 0) && it < it_max) {
         size_t want = (size_t)std::max<double>(256.0, (double)std::max<long>(remaining, 1) * m_draws_per_hit * 1.25);
         want = std::min(want, it_max - it);
-        while (draws_pending() < want) m_draws.push_back(std::rand());
+        draw_until(want);
         size_t consumed = 0;
         uint32_t reverted = 0;
         const int rc = lgca_b200_group_body_force(m_h, (int)remaining, m_draws.data() + m_draw_head, want, &consumed, &reverted);
@@ -267,6 +326,18 @@ void B200_Lattice<model_>::apply_body_force(const int forcing)
         if (consumed == 0) break;
     }
     m_last_consumed = it;
+}
+
+template <Model model_>
+void B200_Lattice<model_>::draw_until(size_t pending)
+{
+    static int bulk_state = 0; // 0 = unchecked, 1 = usable, -1 = not this libc's generator: plain rand()
+    if (m_opt.bulk_rand && bulk_state == 0 && draws_pending() < pending) bulk_state = bulk_rand_selfcheck(m_draws) ? 1 : -1;
+    if (m_opt.bulk_rand && bulk_state == 1 && draws_pending() < pending) {
+        if (bulk_rand_fill(m_draws, pending - draws_pending())) return;
+        bulk_state = -1;
+    }
+    while (draws_pending() < pending) m_draws.push_back(std::rand());
 }
 
 template <Model model_>
@@ -296,6 +367,26 @@ double B200_Lattice<model_>::timed_steps(int n_steps)
     if (rc) fail("timed_steps", rc);
     return ms;
 }
+
+} // namespace lgca
+
+// test hooks (tests/test_bulk_rand.py, no GPU needed): n values of the rand() stream drawn in bulk / the self-check
+extern "C" int lgca_host_bulk_rand(int32_t* out, size_t n)
+{
+    std::vector<int32_t> v;
+    if (!lgca::bulk_rand_fill(v, n)) return 0;
+    std::memcpy(out, v.data(), n * sizeof(int32_t));
+    return 1;
+}
+extern "C" int lgca_host_bulk_rand_selfcheck(int32_t* out32)
+{
+    std::vector<int32_t> v;
+    const bool ok = lgca::bulk_rand_selfcheck(v);
+    std::memcpy(out32, v.data(), 32 * sizeof(int32_t));
+    return ok ? 1 : 0;
+}
+
+namespace lgca {
 
 template class B200_Lattice<Model::HPP>;
 template class B200_Lattice<Model::FHP_I>;

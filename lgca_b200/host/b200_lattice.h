@@ -35,6 +35,11 @@ struct B200Options {
     bool lazy_cell_fields = false; // post_process() leaves the per-cell host fields alone (12 B/cell over PCIe per call);
                                    // sync_cell_fields() computes them from the same output buffer when a writer asks
     bool exact_post  = true;  // reference summation order for the coarse momentum-y means
+    bool bulk_rand = false;      // draw the body-force rand() values in bulk: the state of glibc's default generator (TYPE_3
+                                 // additive feedback, r[i] = r[i-31] + r[i-3]) is borrowed through initstate()/setstate(),
+                                 // advanced by the same recurrence without the per-call lock, and handed back -- the stream and
+                                 // every later rand() call are unchanged (self-checked against rand() on first use; falls back
+                                 // to rand() for any other generator type).  Same caveat as prefetch_draws.
     bool prefetch_draws = false; // get_mean_velocity() starts a helper thread that draws the rand() values the following
                                  // apply_body_force() is expected to consume (glibc rand(): 6-20 ns per draw, ~8 draws per
                                  // reverted particle) while the mean velocity is computed.  The draws enter the same FIFO in
@@ -85,6 +90,7 @@ private:
     std::thread        m_prefetch;            // helper drawing ahead into m_draws (prefetch_draws)
     size_t             m_last_consumed = 0;   // draws the last apply_body_force() consumed
     void               join_prefetch() { if (m_prefetch.joinable()) m_prefetch.join(); }
+    void               draw_until(size_t pending);  // top the FIFO up to `pending` unconsumed draws (rand() or bulk)
     double             m_draws_per_hit = 8.0; // running estimate used to size the draw-ahead
 };
 
