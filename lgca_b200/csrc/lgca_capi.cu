@@ -275,7 +275,7 @@ int lgca_b200_destroy(lgca_b200_lattice* h)
     if (h->s_compute) cudaStreamDestroy(h->s_compute);
     if (h->s_post) cudaStreamDestroy(h->s_post);
     if (h->s_copy) cudaStreamDestroy(h->s_copy);
-    for (int k = 0; k <= LGCA_MAX_K; ++k) cudaFree(h->tile_fluid[k]);
+    for (int k = 0; k <= LGCA_MAX_K; ++k) { cudaFree(h->tile_fluid[k]); cudaFree(h->chain_done[k]); }
     if (h->snap_mutex_init) pthread_mutex_destroy(&h->snap_mutex);
     if (h->ev_snap) cudaEventDestroy(h->ev_snap);
     if (h->ev_post) cudaEventDestroy(h->ev_post);
@@ -417,6 +417,7 @@ static int step_impl(lgca_b200_lattice* h, int n_steps, bool check_halo)
         if (h->snap_spare) { h->planes[h->cur ^ 1] = h->snap_spare; h->snap_spare = nullptr; }
         return 0;
     }
+    int prev_k = 0; // k of the wave launch enqueued right before (0 = none in this call)
     while (n_steps > 0) {
         int k = 1, rc;
         if (!simple) {
@@ -425,8 +426,8 @@ static int step_impl(lgca_b200_lattice* h, int n_steps, bool check_halo)
         }
         uint32_t* in  = h->planes[h->cur];
         uint32_t* out = h->planes[h->cur ^ 1];
-        if (!simple && wave_supported(h, k)) rc = launch_step_wave(h, in, out, k, h->s_compute);
-        else { k = 1; rc = launch_step_simple(h, in, out, h->s_compute); }
+        if (!simple && wave_supported(h, k)) { rc = launch_step_wave(h, in, out, k, h->s_compute, prev_k == k); prev_k = k; }
+        else { k = 1; rc = launch_step_simple(h, in, out, h->s_compute); prev_k = 0; }
         if (rc) return rc;
         h->cur ^= 1;
         if (h->snap_spare) { // `in` is the zero-copy snapshot: the retired snapshot buffer takes its slot in the pair

@@ -78,6 +78,9 @@ struct lgca_b200_lattice {
     int              plan_valid[LGCA_MAX_K + 1];
     uint8_t*         tile_fluid[LGCA_MAX_K + 1];      // per plan: 1 = tile window holds no solid site (wall variants)
     size_t           tile_fluid_cap[LGCA_MAX_K + 1];
+    uint32_t*        chain_done[LGCA_MAX_K + 1];      // per plan: per-chunk completion counters of chained launches (whole lattices)
+    size_t           chain_cap[LGCA_MAX_K + 1];
+    uint32_t         chain_launches[LGCA_MAX_K + 1];  // launches of the plan since its counters were zeroed
     uint64_t         launches;
     uint64_t         device_bytes;
     // native halo ring (lgca_ring.cu)
@@ -132,7 +135,9 @@ struct SnapLock { // scoped lock of snap_mutex (early returns of the CUDA-check 
 // lgca_step_simple.cu : one 32-site word per thread, one step per pass
 int launch_step_simple(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s);
 // lgca_step_wave.cu : register wavefront, k steps per HBM pass
-int launch_step_wave(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
+// chain = the operation enqueued on `s` right before this one is a launch_step_wave of the same handle and k: the launch
+// may start while that one drains (per-chunk completion counters order the data; lgca_step_wave.cu)
+int launch_step_wave(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain = false);
 bool wave_supported(const lgca_b200_lattice* h, int k);
 // lgca_step_resident.cu : the whole lattice in shared memory, n steps per launch (lattices of up to ~20 MB of planes)
 bool resident_supported(const lgca_b200_lattice* h);

@@ -80,12 +80,23 @@ struct WaveArgs {
     const uint8_t*  tile_fluid;        // wall variants: [chunks * bands] 1 = the tile's input window is all fluid (or nullptr)
     uint32_t        stride_bytes;      // distance between consecutive planes of a set (in[d] = in[0] + d * stride)
     uint32_t        mul_two, mul_half; // 2 and 2^31: run-time multipliers of the FMA-pipe funnel shifts (up1/down1)
+    // chained launches (whole lattices): per-chunk completion counters of this plan.  A tile bumps its chunk's counter
+    // when its rows are stored; a tile of the NEXT launch starts as soon as the chunks its input rows lie in have been
+    // completed by all bands of this launch (`chain_target` = launches of this plan so far x bands).
+    uint32_t*       chain_done;        // [chunks] or nullptr
+    uint32_t        chain_target;
 };
 
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
 {
     uint32_t v;
     asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint32_t ld_relaxed_gpu(const uint32_t* p)
+{
+    uint32_t v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
 }
 
@@ -95,8 +106,12 @@ __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p)
 // an interior tile may have pulled into L1 before the push arrived), so those tiles load through L2 (ld.global.cg)
 // after their acquire of the epoch flag.  Interior tiles never touch a ghost row (the prefetch is clamped to the
 // tile's input rows) and keep the faster path.
+// -DLGCA_WAVE_PLAIN_LD=1 (A-B builds): ordinary cached loads (ld.global.ca) instead of the read-only path everywhere.
+#ifndef LGCA_WAVE_PLAIN_LD
+#define LGCA_WAVE_PLAIN_LD 0
+#endif
 template <bool COH>
-__device__ __forceinline__ uint32_t ld_plane(const uint32_t* p) { return COH ? __ldcg(p) : __ldg(p); }
+__device__ __forceinline__ uint32_t ld_plane(const uint32_t* p) { return COH ? __ldcg(p) : (LGCA_WAVE_PLAIN_LD ? __ldca(p) : __ldg(p)); }
 
 // Per-lane view of the periodic row: where this lane's 32 sites come from.
 template <bool IRREG, bool COH = false>
@@ -332,6 +347,49 @@ __device__ __forceinline__ LaneSrc<IRREG, COH> make_lane_src(const Geom& g, int 
     return src;
 }
 
+// Chained launches.  Consecutive launches of one plan on one stream are launched with programmatic stream
+// serialisation and every block releases its dependents first thing, so the tiles of launch n+1 are dispatched into
+// the warp slots the tiles of launch n leave behind -- the staggered end of a launch (3.1: the scheduler serves its
+// warps by strict priority) is filled with the next launch instead of running on half-empty schedulers.  What orders
+// the data is the per-chunk counter: tile (n+1, c) reads rows [oa - K, ob + K) of the planes launch n writes, i.e.
+// rows of the chunks c-1 .. c+1 (periodic), and starts once all bands of those chunks have bumped their counters
+// (release, per lane: stores -> __threadfence -> red.add; acquire, per lane: relaxed poll -> __threadfence, which also
+// drops this SM's L1 lines; the counters count lanes, 32 per tile).  The same wait covers the write-after-read side: tile (n+1, c) writes
+// rows of the buffer launch n READ, and the only launch-n tiles that read those rows are the ones it waited for.
+// Rows a tile reads are not written again before it has bumped its own counter (their next writer is a tile of launch
+// n+2 in the same neighbourhood), so they are constant for the tile's lifetime.  No deadlock: the dependents of a
+// launch are dispatched only after ALL its blocks have started, so whatever a spinning tile waits for is resident or done.
+__device__ __forceinline__ void chain_wait(const WaveArgs& A, const Geom& g, const WavePlan& wp, int c, int K)
+{
+    // every lane polls (same address: one broadcast request) -- no divergent region in front of the tile body
+    int oa, ob;
+    tile_rows(g, wp, c, oa, ob);
+    const int owned = (int)g.rows;                     // whole lattices only (halo = 0, uniform chunks)
+    int n  = min(ob - oa + 2 * K, owned);              // input rows, from row oa - K on (periodic)
+    int ra = oa - K;
+    if (ra < 0) ra += owned;
+    uint32_t ns = 64;
+    while (n > 0) {
+        const int cc  = ra / wp.chunk_rows;
+        const int end = min((cc + 1) * wp.chunk_rows, owned);
+        // relaxed polls with back-off (a waiting tile must not cost the running ones anything); the fence below makes
+        // the successful poll an acquire
+        while ((int32_t)(ld_relaxed_gpu(A.chain_done + cc) - A.chain_target) < 0) {
+            __nanosleep(ns);
+            if (ns < 1024) ns *= 2;
+        }
+        n -= end - ra;
+        ra = end >= owned ? 0 : end;
+    }
+    __threadfence();
+}
+__device__ __forceinline__ void chain_signal(const WaveArgs& A, int c)
+{
+    // every lane publishes its own stores (counters count lanes: 32 per tile)
+    __threadfence();
+    asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(A.chain_done + c) : "memory");
+}
+
 // One tile (band x chunk) of the fused-step kernel.
 template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG, bool COH>
 __device__ __forceinline__ void wave_tile(const WaveArgs& A, const Geom& g, const WavePlan& wp, const int band, const int c)
@@ -339,6 +397,7 @@ __device__ __forceinline__ void wave_tile(const WaveArgs& A, const Geom& g, cons
     constexpr int ND = num_dir_of(MODEL);
     const int lane = threadIdx.x;
     int oa, ob;
+    if (!COH && A.chain_target != 0u) chain_wait(A, g, wp, c, K);
     tile_rows(g, wp, c, oa, ob);
     if (COH) {
         // in-kernel halo wait: only the edge tiles depend on the neighbours' pushes; everyone else starts at once
@@ -408,6 +467,7 @@ __device__ __forceinline__ void wave_tile(const WaveArgs& A, const Geom& g, cons
     }
     if (j < total) LGCA_ROW(0, false, j); // odd number of rows (HPP lattices with odd height)
 #undef LGCA_ROW
+    if (!COH && A.chain_done) chain_signal(A, blockIdx.y);
 }
 
 // The kernel: one warp per block (the tile index and with it every loop bound is provably warp-uniform, so the
@@ -422,6 +482,7 @@ __device__ __forceinline__ void wave_tile(const WaveArgs& A, const Geom& g, cons
 template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
 __global__ void __launch_bounds__(32, wave_min_blocks<MODEL, K, HAS_NS, HAS_SL, IRREG>()) step_wave_kernel(const WaveArgs A, const Geom g, const WavePlan wp)
 {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); // the next chained launch may fill freed warp slots
     const int band = blockIdx.x;
     const int c    = blockIdx.y;
     if (wp.edge_rows && A.ring_flags && c < 2) // edge chunk of a strip on the native ring: flag wait + coherent loads
@@ -529,7 +590,7 @@ bool wave_supported(const lgca_b200_lattice* h, int k)
 #endif
 
 template <int MODEL, int K, bool NS, bool SL, bool IRREG>
-static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s)
+static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s, bool chain)
 {
     auto kernel = step_wave_kernel<MODEL, K, NS, SL, IRREG>;
     if (!h->plan_valid[K]) {
@@ -553,6 +614,32 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
             h->launches++;
             LGCA_CUDA_CHECK(cudaGetLastError());
         }
+        // chained launches: per-chunk completion counters of this plan (whole lattices with uniform chunks)
+        // Chaining pays where one launch fills the machine (C3: +23 %, C5: +4 %).  On smaller lattices the waiting
+        // tiles of the next launches sit in otherwise free warp slots next to the running ones and the launch-to-launch
+        // latency of the counters exceeds the short tail they would hide (measured -15 % .. +20 %, lattice by lattice:
+        // profiles/r03c_chain_sweep.log), so those keep the plain stream order.
+        h->chain_launches[K] = 0;
+        double min_fill = 0.9;
+#ifdef LGCA_B200_TUNING
+        if (getenv("LGCA_B200_CHAIN_MIN_FILL")) min_fill = atof(getenv("LGCA_B200_CHAIN_MIN_FILL"));
+#endif
+        const double slots = (double)(h->sm_count > 0 ? h->sm_count : 148) * (blocks > 0 ? blocks : 16);
+        if (h->g.halo == 0 && h->plans[K].edge_rows == 0 && !(h->cfg.flags & LGCA_B200_FLAG_NO_CHAIN) &&
+            (double)h->plans[K].tiles >= min_fill * slots) {
+            const size_t need = (size_t)h->plans[K].chunks;
+            if (h->chain_cap[K] < need) {
+                if (h->chain_done[K]) cudaFree(h->chain_done[K]);
+                h->chain_done[K] = nullptr; h->chain_cap[K] = 0;
+                LGCA_CUDA_CHECK(cudaMalloc((void**)&h->chain_done[K], need * sizeof(uint32_t)));
+                h->chain_cap[K] = need;
+            }
+            // (stream-ordered behind every earlier launch of the old plan)
+            LGCA_CUDA_CHECK(cudaMemsetAsync(h->chain_done[K], 0, need * sizeof(uint32_t), h->s_compute));
+        } else if (h->chain_done[K]) {
+            cudaFree(h->chain_done[K]);
+            h->chain_done[K] = nullptr; h->chain_cap[K] = 0;
+        }
         h->plan_valid[K] = 1;
     }
     const WavePlan wp = h->plans[K];
@@ -575,74 +662,91 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
         return 0;
     }
     if (wp.chunks > 65535) return set_error(LGCA_B200_EINVAL, "chunk plan exceeds gridDim.y (%d chunks)", wp.chunks);
-    kernel<<<dim3(wp.bands, wp.chunks, 1), dim3(32, 1, 1), 0, s>>>(A, h->g, wp);
+    A.chain_done   = s == h->s_compute ? h->chain_done[K] : nullptr;
+    A.chain_target = h->chain_launches[K] * (uint32_t)wp.bands * 32u; // wraps with the counters (compared as a signed difference)
+    if (A.chain_done && chain) {
+        // the op before this one on `s` is a launch of the same plan: start as its blocks retire (see chain_wait)
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(wp.bands, wp.chunks, 1);
+        cfg.blockDim = dim3(32, 1, 1);
+        cfg.stream = s;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        LGCA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, A, h->g, wp));
+    } else {
+        kernel<<<dim3(wp.bands, wp.chunks, 1), dim3(32, 1, 1), 0, s>>>(A, h->g, wp);
+    }
+    if (A.chain_done) h->chain_launches[K]++;
     h->launches++;
     LGCA_CUDA_CHECK(cudaGetLastError());
     return 0;
 }
 
 template <int MODEL, int K, bool IRREG>
-static int launch_mk(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s)
+static int launch_mk(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, cudaStream_t s, bool chain)
 {
-#define GO(NS, SL) launch_variant<MODEL, K, NS, SL, IRREG>(h, in, out, s)
+#define GO(NS, SL) launch_variant<MODEL, K, NS, SL, IRREG>(h, in, out, s, chain)
     if (h->has_sl) return h->has_ns ? GO(true, true) : GO(false, true);
     return h->has_ns ? GO(true, false) : GO(false, false);
 #undef GO
 }
 
 template <int MODEL, bool IRREG>
-static int launch_m(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s)
+static int launch_m(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain)
 {
     switch (k) {
-    case 1: return launch_mk<MODEL, 1, IRREG>(h, in, out, s);
-    case 2: return launch_mk<MODEL, 2, IRREG>(h, in, out, s);
-    case 3: return launch_mk<MODEL, 3, IRREG>(h, in, out, s);
-    case 4: return launch_mk<MODEL, 4, IRREG>(h, in, out, s);
-    case 5: return launch_mk<MODEL, 5, IRREG>(h, in, out, s);
-    case 6: return launch_mk<MODEL, 6, IRREG>(h, in, out, s);
-    case 7: if (MODEL == MODEL_HPP) return launch_mk<MODEL_HPP, 7, IRREG>(h, in, out, s); break;
-    case 8: if (MODEL == MODEL_HPP) return launch_mk<MODEL_HPP, 8, IRREG>(h, in, out, s); break;
+    case 1: return launch_mk<MODEL, 1, IRREG>(h, in, out, s, chain);
+    case 2: return launch_mk<MODEL, 2, IRREG>(h, in, out, s, chain);
+    case 3: return launch_mk<MODEL, 3, IRREG>(h, in, out, s, chain);
+    case 4: return launch_mk<MODEL, 4, IRREG>(h, in, out, s, chain);
+    case 5: return launch_mk<MODEL, 5, IRREG>(h, in, out, s, chain);
+    case 6: return launch_mk<MODEL, 6, IRREG>(h, in, out, s, chain);
+    case 7: if (MODEL == MODEL_HPP) return launch_mk<MODEL_HPP, 7, IRREG>(h, in, out, s, chain); break;
+    case 8: if (MODEL == MODEL_HPP) return launch_mk<MODEL_HPP, 8, IRREG>(h, in, out, s, chain); break;
     }
     return set_error(LGCA_B200_EINVAL, "unsupported k_fuse %d", k);
 }
 
 // The kernel variants are spread over six translation units (collision rule x regular/irregular width) that the
 // build compiles in parallel: -DLGCA_WAVE_TU=0..5 selects one, no define = everything in one unit.
-int launch_wave_hpp_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
-int launch_wave_hpp_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
-int launch_wave_fhp1_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
-int launch_wave_fhp1_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
-int launch_wave_fhp2_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
-int launch_wave_fhp2_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s);
+int launch_wave_hpp_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain);
+int launch_wave_hpp_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain);
+int launch_wave_fhp1_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain);
+int launch_wave_fhp1_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain);
+int launch_wave_fhp2_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain);
+int launch_wave_fhp2_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain);
 #if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 0
-int launch_wave_hpp_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s) { return launch_m<MODEL_HPP, false>(h, in, out, k, s); }
+int launch_wave_hpp_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain) { return launch_m<MODEL_HPP, false>(h, in, out, k, s, chain); }
 #endif
 #if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 1
-int launch_wave_hpp_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s) { return launch_m<MODEL_HPP, true>(h, in, out, k, s); }
+int launch_wave_hpp_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain) { return launch_m<MODEL_HPP, true>(h, in, out, k, s, chain); }
 #endif
 #if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 2
-int launch_wave_fhp1_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s) { return launch_m<MODEL_FHP_I, false>(h, in, out, k, s); }
+int launch_wave_fhp1_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain) { return launch_m<MODEL_FHP_I, false>(h, in, out, k, s, chain); }
 #endif
 #if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 3
-int launch_wave_fhp1_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s) { return launch_m<MODEL_FHP_I, true>(h, in, out, k, s); }
+int launch_wave_fhp1_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain) { return launch_m<MODEL_FHP_I, true>(h, in, out, k, s, chain); }
 #endif
 #if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 4
-int launch_wave_fhp2_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s) { return launch_m<MODEL_FHP_II, false>(h, in, out, k, s); }
+int launch_wave_fhp2_reg(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain) { return launch_m<MODEL_FHP_II, false>(h, in, out, k, s, chain); }
 #endif
 #if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 5
-int launch_wave_fhp2_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s) { return launch_m<MODEL_FHP_II, true>(h, in, out, k, s); }
+int launch_wave_fhp2_irr(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain) { return launch_m<MODEL_FHP_II, true>(h, in, out, k, s, chain); }
 #endif
 
 #if !defined(LGCA_WAVE_TU) || LGCA_WAVE_TU == 0
-int launch_step_wave(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s)
+int launch_step_wave(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, int k, cudaStream_t s, bool chain)
 {
     if ((uint64_t)h->g.rows * h->g.pitch > 0xFFFFFFFFull || (uint64_t)h->g.plane_stride * sizeof(uint32_t) > 0xFFFFFFFFull)
         return set_error(LGCA_B200_EINVAL, "plane too large for 32-bit word offsets");
     const bool irreg = h->g.rem != 0;
     switch (rule_of(h->cfg.model)) {
-    case MODEL_HPP:   return irreg ? launch_wave_hpp_irr(h, in, out, k, s) : launch_wave_hpp_reg(h, in, out, k, s);
-    case MODEL_FHP_I: return irreg ? launch_wave_fhp1_irr(h, in, out, k, s) : launch_wave_fhp1_reg(h, in, out, k, s);
-    default:          return irreg ? launch_wave_fhp2_irr(h, in, out, k, s) : launch_wave_fhp2_reg(h, in, out, k, s);
+    case MODEL_HPP:   return irreg ? launch_wave_hpp_irr(h, in, out, k, s, chain) : launch_wave_hpp_reg(h, in, out, k, s, chain);
+    case MODEL_FHP_I: return irreg ? launch_wave_fhp1_irr(h, in, out, k, s, chain) : launch_wave_fhp1_reg(h, in, out, k, s, chain);
+    default:          return irreg ? launch_wave_fhp2_irr(h, in, out, k, s, chain) : launch_wave_fhp2_reg(h, in, out, k, s, chain);
     }
 }
 
@@ -650,7 +754,7 @@ int launch_step_wave(lgca_b200_lattice* h, const uint32_t* in, uint32_t* out, in
 bool wave_has_edge_chunks(lgca_b200_lattice* h, int k)
 {
     if (!wave_supported(h, k)) return false;
-    if (!h->plan_valid[k] && launch_step_wave(h, nullptr, nullptr, k, 0) != 0) return false;
+    if (!h->plan_valid[k] && launch_step_wave(h, nullptr, nullptr, k, 0, false) != 0) return false;
     // The spinning edge tiles are scheduled first.  If they alone could fill the resident-block capacity of the device,
     // the push kernel of the previous block (which the NEIGHBOUR's edge tiles wait for) might never be dispatched and
     // the ring would hang: very wide strips fall back to the stream-ordered wait kernel.
@@ -666,7 +770,7 @@ int wave_prepare(lgca_b200_lattice* h)
 {
     for (int k = 1; k <= h->k_fuse; ++k) {
         if (!wave_supported(h, k)) continue;
-        const int rc = launch_step_wave(h, nullptr, nullptr, k, 0);
+        const int rc = launch_step_wave(h, nullptr, nullptr, k, 0, false);
         if (rc) return rc;
     }
     return 0;
