@@ -64,9 +64,11 @@ enum {
                                                 device-side prefix (A-B tests; row strips always take this route) */
     LGCA_B200_FLAG_RESIDENT_DYNAMIC = 1u << 5,/* SM-resident kernel: dynamic four-word groups instead of static word ownership
                                                 (A-B tests; the mapping of lattices with > 8192 words per CTA anyway) */
-    LGCA_B200_FLAG_NO_CHAIN       = 1u << 6  /* wavefront kernel: consecutive launches of one lgca_b200_step call strictly one
+    LGCA_B200_FLAG_NO_CHAIN       = 1u << 6, /* wavefront kernel: consecutive launches of one lgca_b200_step call strictly one
                                                 after the other instead of chained (the next launch filling the warp slots the
                                                 previous one frees, ordered by per-chunk completion counters); A-B tests */
+    LGCA_B200_FLAG_FORCE_CHAIN    = 1u << 7  /* chain launches also where one launch does not fill the machine (the library's
+                                                own choice there is the plain stream order); tests of the chain on small lattices */
 };
 
 typedef struct lgca_b200_lattice lgca_b200_lattice; /* opaque */

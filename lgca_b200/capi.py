@@ -16,6 +16,7 @@ FLAG_FORCE_RESIDENT = 1 << 3
 FLAG_HOST_BODY_FORCE = 1 << 4
 FLAG_RESIDENT_DYNAMIC = 1 << 5
 FLAG_NO_CHAIN = 1 << 6
+FLAG_FORCE_CHAIN = 1 << 7
 
 # every symbol include/lgca_b200.h declares (checked by tests/test_capi_symbols.py)
 SYMBOLS = [

@@ -232,10 +232,13 @@ int lgca_b200_group_step(lgca_b200_group* g, int n_steps)
         if ((rc = lgca_b200_steps_per_exchange(h, &b))) return rc;
         block = std::min(block, b);
     }
+    bool first = true;
     while (n_steps > 0) { // block-major: see the top of the file
         const int k = std::min(block, n_steps);
+        // nothing else touches a strip's compute stream between two blocks of this loop: launches may be chained
         for (lgca_b200_lattice* h : g->strips)
-            if ((rc = lgca_b200_ring_step(h, k))) return rc;
+            if ((rc = ring_step_blocks(h, k, !first))) return rc;
+        first = false;
         n_steps -= k;
     }
     return 0;

@@ -95,6 +95,8 @@ struct lgca_b200_lattice {
     uint32_t         ring_epoch;
     uint64_t         ring_blocks;           // blocks issued since ring_start
     uint32_t         ring_inkernel_epoch;   // != 0: the next wave launch waits in-kernel for this epoch
+    int              ring_chain_k;          // k of the wave launch that ended the last ring_step_blocks call (0 = not chainable)
+    int              ring_chain_run;        // chained launches in a row so far
     cudaStream_t     s_ring;                // pushes + signals run here, overlapped with the next step kernel
     cudaEvent_t      ev_step[2], ev_push[2];
     // SM-resident kernel (lgca_step_resident.cu): ghost-row exchange area between CTAs and their progress counters
@@ -146,6 +148,8 @@ int resident_info(const lgca_b200_lattice* h, int* ctas, int* steps_per_exchange
 int wave_prepare(lgca_b200_lattice* h);
 bool wave_has_edge_chunks(lgca_b200_lattice* h, int k);
 int simple_prepare(lgca_b200_lattice* h);
+int ring_step_blocks(lgca_b200_lattice* h, int n_steps, bool continue_chain); // lgca_ring.cu: lgca_b200_ring_step + chain hint
+int step_one_launch(lgca_b200_lattice* h, int k, bool chain); // lgca_capi.cu: k <= steps_per_launch steps of a strip in ONE wave launch
 int ring_wait_current_epoch(lgca_b200_lattice* h); // lgca_ring.cu: stream-ordered wait for the neighbours' latest pushes
 int ring_order_inplace_write(lgca_b200_lattice* h); // lgca_ring.cu: the compute stream waits for my last ghost-row push
 int unalias_snapshot(lgca_b200_lattice* h); // lgca_capi.cu: give the live state a buffer of its own before an in-place write

@@ -44,6 +44,7 @@ struct RingBlob { // what a rank publishes to its neighbours
     cudaIpcMemHandle_t ipc_flags;
 };
 static const uint64_t RING_MAGIC = 0x4C47434152494E47ull; // "LGCARING"
+static const int      RING_CHAIN_DEPTH = 2;                 // chained launches in a row on a strip (lgca_b200::ring_step_blocks)
 
 // copies `halo` rows of every plane: src rows [src_row, src_row+halo) -> dst rows [dst_row, ...)
 __global__ void __launch_bounds__(256) ring_push_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst_upper,
@@ -68,12 +69,15 @@ __global__ void __launch_bounds__(256) ring_push_kernel(const uint32_t* __restri
 }
 
 __global__ void ring_signal_kernel(volatile uint32_t* upper_flag_from_lower, volatile uint32_t* lower_flag_from_upper,
-                                   uint32_t epoch)
+                                   uint32_t epoch, volatile uint32_t* my_push_done)
 {
     __threadfence_system();
     // the upper neighbour sees me as its LOWER neighbour (flag slot 0), the lower one as its UPPER (slot 1)
     *upper_flag_from_lower = epoch;
     *lower_flag_from_upper = epoch;
+    // my own slot 4: the push of this epoch has read my edge rows (edge tiles of chained launches wait for it before
+    // they overwrite those rows)
+    if (my_push_done) *my_push_done = epoch;
     __threadfence_system();
 }
 
@@ -97,7 +101,7 @@ static int ring_push_and_signal(lgca_b200_lattice* h, cudaStream_t s)
     LGCA_CUDA_CHECK(cudaGetLastError());
     h->ring_epoch++;
     ring_signal_kernel<<<1, 1, 0, s>>>((volatile uint32_t*)h->ring_upper_flags + 0, (volatile uint32_t*)h->ring_lower_flags + 1,
-                                       h->ring_epoch);
+                                       h->ring_epoch, (volatile uint32_t*)h->ring_flags + 4);
     h->launches++;
     LGCA_CUDA_CHECK(cudaGetLastError());
     return 0;
@@ -249,7 +253,7 @@ int lgca_b200_ring_republish(lgca_b200_lattice* h)
     const uint32_t next = h->ring_epoch + 1;
     // my compute stream has passed every reader of my ghost rows (step kernels, snapshot side copies): tell the
     // neighbours they may overwrite them; slot 2 = ack from the lower neighbour, slot 3 = from the upper one
-    ring_signal_kernel<<<1, 1, 0, h->s_compute>>>((volatile uint32_t*)h->ring_upper_flags + 2, (volatile uint32_t*)h->ring_lower_flags + 3, next);
+    ring_signal_kernel<<<1, 1, 0, h->s_compute>>>((volatile uint32_t*)h->ring_upper_flags + 2, (volatile uint32_t*)h->ring_lower_flags + 3, next, nullptr);
     h->launches++;
     LGCA_CUDA_CHECK(cudaGetLastError());
     ring_wait_kernel<<<1, 2, 0, h->s_compute>>>((volatile uint32_t*)h->ring_flags + 2, next);
@@ -264,7 +268,11 @@ int lgca_b200_ring_republish(lgca_b200_lattice* h)
 // First publish after upload / init and connect, before the first lgca_b200_ring_step (kept as its own entry point).
 int lgca_b200_ring_start(lgca_b200_lattice* h) { return lgca_b200_ring_republish(h); }
 
-int lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps)
+} // extern "C"
+
+// continue_chain: the caller guarantees that nothing was enqueued on this strip's compute stream since the last block of
+// its previous ring_step_blocks call (lgca_group.cu: the block-major loop of one group_step)
+int lgca_b200::ring_step_blocks(lgca_b200_lattice* h, int n_steps, bool continue_chain)
 {
     if (!h) return set_error(LGCA_B200_EINVAL, "null handle");
     if (!h->ring_connected) return set_error(LGCA_B200_ESTATE, "ring not connected");
@@ -273,18 +281,30 @@ int lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps)
     LGCA_CUDA_CHECK(cudaSetDevice(h->cfg.device));
     // one kernel launch per exchange: the fused depth of the wavefront kernel, or 1 for the generic kernel
     const int block = std::min(steps_per_launch(h, h->k_fuse), (int)h->g.halo);
+    int prev_k = continue_chain ? h->ring_chain_k : 0; // k of the in-kernel-wait wave launch enqueued right before (0 = none)
     while (n_steps > 0) {
         const int k = n_steps < block ? n_steps : block;
         const int slot = (int)(h->ring_blocks & 1u);
+        const bool inkernel = !(h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) && wave_has_edge_chunks(h, k);
+        // chained launch (lgca_step_wave.cu): the step kernel may start while the previous one drains, so nothing may sit
+        // between the two on the compute stream but event records -- the WAR wait below moves into the edge tiles
+        // At most RING_CHAIN_DEPTH launches in a row are chained, then one is stream-ordered again: tiles of chained
+        // launches that (transitively) wait for a neighbour's push spin in warp slots, and the pushes themselves need a
+        // slot on their GPU -- the bound keeps the spinners of a strip that runs ahead of its neighbours to a fraction
+        // of the machine (bands x depth x (depth + 1) tiles), whatever the neighbours' host threads are doing.
+        const bool chain = inkernel && prev_k == k && h->chain_done[k] != nullptr && h->ring_chain_run < RING_CHAIN_DEPTH;
+        h->ring_chain_run = chain ? h->ring_chain_run + 1 : 0;
         // (WAR) this block overwrites edge rows that an earlier push read (pushes complete in order on s_ring)
-        if (h->ring_blocks >= 2) LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_push[slot], 0));
+        if (!chain && h->ring_blocks >= 2) LGCA_CUDA_CHECK(cudaStreamWaitEvent(h->s_compute, h->ev_push[slot], 0));
         int rc;
-        if (!(h->cfg.flags & LGCA_B200_FLAG_SIMPLE_KERNEL) && wave_has_edge_chunks(h, k)) {
+        if (inkernel) {
             // tiles that read ghost rows wait in-kernel; the rest of the strip starts immediately
             h->ring_inkernel_epoch = h->ring_epoch;
-            rc = lgca_b200_step(h, k);
+            rc = step_one_launch(h, k, chain);
             h->ring_inkernel_epoch = 0;
+            prev_k = k;
         } else {
+            prev_k = 0;
             ring_wait_kernel<<<1, 2, 0, h->s_compute>>>((volatile uint32_t*)h->ring_flags, h->ring_epoch);
             h->launches++;
             LGCA_CUDA_CHECK(cudaGetLastError());
@@ -299,8 +319,13 @@ int lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps)
         h->ring_blocks++;
         n_steps -= k;
     }
+    h->ring_chain_k = prev_k;
     return 0;
 }
+
+extern "C" {
+
+int lgca_b200_ring_step(lgca_b200_lattice* h, int n_steps) { return lgca_b200::ring_step_blocks(h, n_steps, false); }
 
 int lgca_b200_ring_disconnect(lgca_b200_lattice* h)
 {

@@ -75,8 +75,9 @@ struct WaveArgs {
     const uint32_t* ch;
     const uint32_t* xedge;
     // native ring: tiles that read ghost rows spin until the neighbours have published `ring_epoch`
-    const uint32_t* ring_flags; // [0] from the lower neighbour, [1] from the upper; nullptr = no in-kernel wait
+    const uint32_t* ring_flags; // [0] from the lower neighbour, [1] from the upper, [4] my own last completed push; nullptr = no in-kernel wait
     uint32_t        ring_epoch;
+    uint32_t        ring_push_epoch;   // edge tiles overwrite rows my push of this epoch read: wait until it has completed
     const uint8_t*  tile_fluid;        // wall variants: [chunks * bands] 1 = the tile's input window is all fluid (or nullptr)
     uint32_t        stride_bytes;      // distance between consecutive planes of a set (in[d] = in[0] + d * stride)
     uint32_t        mul_two, mul_half; // 2 and 2^31: run-time multipliers of the FMA-pipe funnel shifts (up1/down1)
@@ -297,7 +298,27 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG, 
 template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
 constexpr int wave_min_blocks()
 {
-    return (rule_of(MODEL) != MODEL_HPP && !HAS_NS && !HAS_SL && !IRREG && K <= 5) ? LGCA_WAVE_MIN_BLOCKS : 0; // 0 = no hint
+    if (rule_of(MODEL) != MODEL_HPP && !HAS_NS && !HAS_SL && !IRREG && K <= 5) return LGCA_WAVE_MIN_BLOCKS;
+    // Occupancy pins: the prologue / epilogue of chained launches (chain_wait / chain_signal) nudged the register
+    // allocation of a few rarely used variants over an occupancy step (64 -> 66 registers and the like); these keep the
+    // class they had where that costs no spill (-Xptxas -v); HPP K4 ns+sl, K5 sl and K7 ns run one warp per scheduler lower.
+    constexpr int  R   = rule_of(MODEL);
+    constexpr bool NS = HAS_NS, SL = HAS_SL;
+    if (R == MODEL_HPP && !IRREG) {
+        if ((K == 3 && NS && SL) || (K == 4 && NS && !SL)) return 32;
+        if ((K == 6 && NS && !SL) || (K == 7 && !NS && SL)) return 28;
+    }
+    if (R == MODEL_HPP && IRREG) {
+        if (K == 4 && NS && SL) return 24;
+        if (K == 6 && NS && SL) return 20;
+        if (K == 7 && !NS && !SL) return 28;
+    }
+    if (R == MODEL_FHP_I && IRREG) {
+        if (K == 2 && NS && SL) return 28;
+        if (K == 4 && !NS && !SL) return 24;
+    }
+    if (R == MODEL_FHP_II && !IRREG && K == 6 && NS && SL) return 16;
+    return 0; // no hint
 }
 // Row range [oa, ob) of a tile's output, relative to the first owned row.  Whole lattices: uniform chunks.
 // Strips: tile rows 0 and 1 are the bottom and the top EDGE chunk (the only ones that read ghost rows); they are
@@ -359,19 +380,29 @@ __device__ __forceinline__ LaneSrc<IRREG, COH> make_lane_src(const Geom& g, int 
 // Rows a tile reads are not written again before it has bumped its own counter (their next writer is a tile of launch
 // n+2 in the same neighbourhood), so they are constant for the tile's lifetime.  No deadlock: the dependents of a
 // launch are dispatched only after ALL its blocks have started, so whatever a spinning tile waits for is resident or done.
-__device__ __forceinline__ void chain_wait(const WaveArgs& A, const Geom& g, const WavePlan& wp, int c, int K)
+static __device__ __noinline__ void chain_wait(const WaveArgs& A, const Geom& g, const WavePlan& wp, int c, int K)
 {
     // every lane polls (same address: one broadcast request) -- no divergent region in front of the tile body
     int oa, ob;
     tile_rows(g, wp, c, oa, ob);
-    const int owned = (int)g.rows;                     // whole lattices only (halo = 0, uniform chunks)
-    int n  = min(ob - oa + 2 * K, owned);              // input rows, from row oa - K on (periodic)
+    const int owned = (int)(g.rows - 2 * g.halo);
+    const int E     = wp.edge_rows;
+    int n  = ob - oa + 2 * K;                          // input rows, from row oa - K on
     int ra = oa - K;
-    if (ra < 0) ra += owned;
+    if (E == 0) {                                      // whole lattice: periodic
+        n = min(n, owned);
+        if (ra < 0) ra += owned;
+    } else {                                           // strip: ghost rows are covered by the neighbours' epoch flags
+        if (ra < 0) { n += ra; ra = 0; }
+        n = min(n, owned - ra);
+    }
     uint32_t ns = 64;
     while (n > 0) {
-        const int cc  = ra / wp.chunk_rows;
-        const int end = min((cc + 1) * wp.chunk_rows, owned);
+        int cc, end;                                   // chunk of row ra and its last row + 1 (tile_rows inverted)
+        if (E == 0)               { cc = ra / wp.chunk_rows; end = min((cc + 1) * wp.chunk_rows, owned); }
+        else if (ra < E)          { cc = 0; end = E; }
+        else if (ra >= owned - E) { cc = 1; end = owned; }
+        else                      { cc = 2 + (ra - E) / wp.chunk_rows; end = min(E + (cc - 1) * wp.chunk_rows, owned - E); }
         // relaxed polls with back-off (a waiting tile must not cost the running ones anything); the fence below makes
         // the successful poll an acquire
         while ((int32_t)(ld_relaxed_gpu(A.chain_done + cc) - A.chain_target) < 0) {
@@ -379,11 +410,11 @@ __device__ __forceinline__ void chain_wait(const WaveArgs& A, const Geom& g, con
             if (ns < 1024) ns *= 2;
         }
         n -= end - ra;
-        ra = end >= owned ? 0 : end;
+        ra = (E == 0 && end >= owned) ? 0 : end;
     }
     __threadfence();
 }
-__device__ __forceinline__ void chain_signal(const WaveArgs& A, int c)
+static __device__ __noinline__ void chain_signal(const WaveArgs& A, int c)
 {
     // every lane publishes its own stores (counters count lanes: 32 per tile)
     __threadfence();
@@ -397,13 +428,16 @@ __device__ __forceinline__ void wave_tile(const WaveArgs& A, const Geom& g, cons
     constexpr int ND = num_dir_of(MODEL);
     const int lane = threadIdx.x;
     int oa, ob;
-    if (!COH && A.chain_target != 0u) chain_wait(A, g, wp, c, K);
+    if (A.chain_target != 0u) chain_wait(A, g, wp, c, K);
     tile_rows(g, wp, c, oa, ob);
     if (COH) {
         // in-kernel halo wait: only the edge tiles depend on the neighbours' pushes; everyone else starts at once
         if (lane == 0) {
             if (c == 0) while (ld_acquire_sys(A.ring_flags + 0) < A.ring_epoch) __nanosleep(64);
             else        while (ld_acquire_sys(A.ring_flags + 1) < A.ring_epoch) __nanosleep(64);
+            // (WAR) the rows this tile stores were read by my own ghost-row push two blocks ago (chained launches: the
+            // stream does not order this launch behind that push any more)
+            while ((int32_t)(ld_acquire_sys(A.ring_flags + 4) - A.ring_push_epoch) < 0) __nanosleep(64);
         }
         __syncwarp();
     }
@@ -467,7 +501,7 @@ __device__ __forceinline__ void wave_tile(const WaveArgs& A, const Geom& g, cons
     }
     if (j < total) LGCA_ROW(0, false, j); // odd number of rows (HPP lattices with odd height)
 #undef LGCA_ROW
-    if (!COH && A.chain_done) chain_signal(A, blockIdx.y);
+    if (A.chain_done) chain_signal(A, blockIdx.y);
 }
 
 // The kernel: one warp per block (the tile index and with it every loop bound is provably warp-uniform, so the
@@ -543,6 +577,9 @@ static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
     const char* e_res = nullptr;
 #endif
     const double resident = e_res ? atof(e_res) : (double)resident_warps;
+    // chained launches (whole lattices) hide most of the staggered end of a launch behind the next one (C5 with chaining:
+    // 246-row chunks = 2 rounds 1.230e13, 164 rows = 3 rounds 1.226e13, 490 rows = 1 round 1.13e13)
+    const double tail = !(h->cfg.flags & LGCA_B200_FLAG_NO_CHAIN) ? 0.10 : 0.15;
     int    best_cr = (rows + 1) & ~1;
     double best = 1e300;
     for (int cr = 2 * k; cr <= rows + 1; cr += 2) {
@@ -551,7 +588,7 @@ static WavePlan make_plan(const lgca_b200_lattice* h, int k, int resident_warps)
         const double w      = (double)chunks * wp.bands / (double)(h->sm_count > 0 ? h->sm_count : 148); // warps per SM
         const double rounds = fmax(1.0, ceil(w / resident));
         const double eff    = pow(fmin(1.0, (w / rounds) / resident), 0.6);
-        const double cost   = (double)(cr + k - 1 + 3) * (rounds + 0.15) / eff;
+        const double cost   = (double)(cr + k - 1 + 3) * (rounds + tail) / eff;
         if (cost <= best) { best = cost; best_cr = cr; }
     }
     int cr = best_cr;
@@ -625,8 +662,8 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
         if (getenv("LGCA_B200_CHAIN_MIN_FILL")) min_fill = atof(getenv("LGCA_B200_CHAIN_MIN_FILL"));
 #endif
         const double slots = (double)(h->sm_count > 0 ? h->sm_count : 148) * (blocks > 0 ? blocks : 16);
-        if (h->g.halo == 0 && h->plans[K].edge_rows == 0 && !(h->cfg.flags & LGCA_B200_FLAG_NO_CHAIN) &&
-            (double)h->plans[K].tiles >= min_fill * slots) {
+        if ((h->g.halo == 0 || h->plans[K].edge_rows > 0) && !(h->cfg.flags & LGCA_B200_FLAG_NO_CHAIN) &&
+            ((double)h->plans[K].tiles >= min_fill * slots || (h->cfg.flags & LGCA_B200_FLAG_FORCE_CHAIN))) {
             const size_t need = (size_t)h->plans[K].chunks;
             if (h->chain_cap[K] < need) {
                 if (h->chain_done[K]) cudaFree(h->chain_done[K]);
@@ -652,6 +689,7 @@ static int launch_variant(lgca_b200_lattice* h, const uint32_t* in, uint32_t* ou
     A.ns = h->ns; A.sl = h->sl; A.ch = h->ch; A.xedge = h->xedge;
     A.ring_flags = h->ring_inkernel_epoch ? (const uint32_t*)h->ring_flags : nullptr;
     A.ring_epoch = h->ring_inkernel_epoch;
+    A.ring_push_epoch = h->ring_inkernel_epoch ? h->ring_inkernel_epoch - 1u : 0u; // epoch = pushes issued; the one before the last
     A.mul_two = 2u; A.mul_half = 0x80000000u;
     A.stride_bytes = (uint32_t)(h->g.plane_stride * sizeof(uint32_t));
     A.tile_fluid = (NS || SL) ? h->tile_fluid[K] : nullptr;

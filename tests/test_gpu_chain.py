@@ -11,6 +11,7 @@ pytestmark = pytest.mark.gpu
 
 NO_RESIDENT = 4
 NO_CHAIN = 64
+FORCE_CHAIN = 128   # the library chains on its own only where one launch fills the machine (>= ~20 M sites)
 
 
 def _engine(o, k_fuse, flags):
@@ -40,7 +41,7 @@ def test_chained_launches_match_oracle(case):
     o = Oracle(model, dims=dims, cg=1, rng=OracleRng(11))
     o.apply_bc(bc)
     o.init("random")
-    e = _engine(o, k, NO_RESIDENT)
+    e = _engine(o, k, NO_RESIDENT | FORCE_CHAIN)
     s = _engine(o, k, NO_RESIDENT | NO_CHAIN)
     for n in (steps, 2 * k, steps):
         e.step(n)
@@ -62,7 +63,7 @@ def test_chain_across_snapshots_and_mask_upload():
     o = Oracle("FHP_III", dims=(1024, 512), cg=4, rng=OracleRng(3))
     o.apply_bc("pipe")
     o.init("random")
-    e = _engine(o, 4, NO_RESIDENT)
+    e = _engine(o, 4, NO_RESIDENT | FORCE_CHAIN)
     for n in (17, 9, 30):
         e.step(n); o.step(n)
         e.snapshot(); o.snapshot()
@@ -89,7 +90,7 @@ def test_chain_equals_serial_at_config_size(cfg):
     model, dx, dy, bc, k, steps = cfg
     hashes = []
     n0 = None
-    for flags in (NO_RESIDENT, NO_RESIDENT | NO_CHAIN, NO_RESIDENT):
+    for flags in (NO_RESIDENT | FORCE_CHAIN, NO_RESIDENT | NO_CHAIN, NO_RESIDENT):
         e = lgca_b200.Engine(model, dx, dy, k_fuse=k, flags=flags)
         e.apply_bc_device(bc)
         e.init_random_device(seed=5)
@@ -102,3 +103,58 @@ def test_chain_equals_serial_at_config_size(cfg):
         hashes.append(hs)
         e.close()
     assert hashes[0] == hashes[1] == hashes[2]
+
+
+# Row strips: chained blocks of the native ring (the write-after-read wait for my own ghost-row push moves from the stream
+# into the edge tiles).  Strips share device 0 here (plain peer pointers); bench.py checks the same invariance across real
+# GPUs in every multi-GPU run (multi_gpu_parity).
+STRIP_CASES = [
+    ("FHP_III", (2048, 768), "periodic", 6, [0, 0], 50),
+    ("FHP_III", (1024, 960), "karman", 4, [0, 0, 0], 45),
+    ("FHP_II", (2048, 512), "reflecting_back", 6, [0, 0], 37),
+    ("HPP", (1024, 600), "reflecting_forward", 6, [0, 0, 0], 61),
+    ("FHP_I", (1400, 700), "pipe", 5, [0, 0], 26),
+]
+
+
+@pytest.mark.parametrize("case", STRIP_CASES, ids=lambda c: "%s-%dx%d-%s-k%d-%dstrips" % (c[0], c[1][0], c[1][1], c[2], c[3], len(c[4])))
+def test_chained_strips_match_oracle(case):
+    import lgca_b200
+    model, dims, bc, k, devs, steps = case
+    o = Oracle(model, dims=dims, cg=1, rng=OracleRng(13))
+    o.apply_bc(bc)
+    o.init("random")
+    g = lgca_b200.Group(model, dims[0], dims[1], n_gpus=len(devs), dev_ids=devs, k_fuse=k, flags=FORCE_CHAIN)
+    g.upload(o.state, o.cell_type, o.rnd)
+    for n in (steps, 1, 3 * k, steps):
+        g.step(n)
+        o.step(n)
+        got = g.download()
+        if not np.array_equal(got, o.state):
+            bad = np.nonzero(got != o.state)[0]
+            raise AssertionError("chained strips differ after +%d steps: %d cells, first at (x=%d,y=%d)" % (
+                n, bad.size, bad[0] % o.dim_x, bad[0] // o.dim_x))
+        g.snapshot()   # rotates the three plane sets on every strip
+    assert g.count_particles() == o.n_particles()
+    g.close()
+
+
+def test_chained_strips_equal_whole_lattice_at_size():
+    """8192 x 8192 FHP-III with walls as 2 strips (chained by the library's own choice) vs one whole lattice, serial."""
+    import lgca_b200
+    dx, dy = 8192, 8192
+    hashes = []
+    for kind in ("strips", "whole"):
+        if kind == "strips":
+            e = lgca_b200.Group("FHP_III", dx, dy, n_gpus=2, dev_ids=[0, 0])
+        else:
+            e = lgca_b200.Engine("FHP_III", dx, dy, flags=NO_CHAIN)
+        e.apply_bc_device("karman")
+        e.init_random_device(seed=9)
+        hs = []
+        for _ in range(2):
+            e.step(97)
+            hs.append(fnv1a64(e.download()))
+        hashes.append(hs)
+        e.close()
+    assert hashes[0] == hashes[1]
