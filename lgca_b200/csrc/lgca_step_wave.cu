@@ -30,6 +30,7 @@
 #include <stdlib.h>
 
 #include "lgca_internal.h"
+#include "lgca_wave_pins.h"
 
 namespace lgca_b200 {
 
@@ -287,38 +288,18 @@ __device__ __forceinline__ void wave_row(WaveState<K>& st, const LaneSrc<IRREG, 
 }
 
 // Register cap via the resident-blocks hint.  One-warp blocks are spread over the four SM sub-partitions of 16384
-// registers each, so the occupancy steps are 128 registers -> 4 warps per sub-partition, 96 -> 5, 80 -> 6.  The
-// all-fluid FHP variants (K <= 5) fit 96 registers with at most two spilled words, which lifts them from 4 to 5
+// registers each, so the occupancy steps are 128 registers -> 4 warps per sub-partition, 96 -> 5, 80 -> 6, 72 -> 7, 64 -> 8.
+// The all-fluid FHP variants (K <= 5) fit 96 registers with at most two spilled words, which lifts them from 4 to 5
 // resident warps per scheduler (+7 % measured).  Measured and rejected: K = 6 at 96 registers (11 spilled words,
-// -1.4 %), the wall variants at 96 (33-43 spilled words, -11 %), K = 4 at 80 registers (-4 %); HPP needs only 64.
-// Those variants carry no hint (0).
-#ifndef LGCA_WAVE_MIN_BLOCKS
-#define LGCA_WAVE_MIN_BLOCKS 20
-#endif
+// -1.4 %), the wall variants at 96 (33-43 spilled words, -11 %), K = 4 at 80 registers (-4 %).
+// The prologue / epilogue of chained launches (chain_wait / chain_signal, the ring's push wait) nudges ptxas over an
+// occupancy step in about two dozen of the 160 variants, so every variant is pinned to the class it had without them
+// (lgca_wave_pins.h, generated by scripts/gen_wave_pins.py from the ptxas log of the pre-chain build,
+// profiles/r03_wave_ptxas_before_chain.log); variants the pin would make spill run one class lower instead.
 template <int MODEL, int K, bool HAS_NS, bool HAS_SL, bool IRREG>
 constexpr int wave_min_blocks()
 {
-    if (rule_of(MODEL) != MODEL_HPP && !HAS_NS && !HAS_SL && !IRREG && K <= 5) return LGCA_WAVE_MIN_BLOCKS;
-    // Occupancy pins: the prologue / epilogue of chained launches (chain_wait / chain_signal) nudged the register
-    // allocation of a few rarely used variants over an occupancy step (64 -> 66 registers and the like); these keep the
-    // class they had where that costs no spill (-Xptxas -v); HPP K4 ns+sl, K5 sl and K7 ns run one warp per scheduler lower.
-    constexpr int  R   = rule_of(MODEL);
-    constexpr bool NS = HAS_NS, SL = HAS_SL;
-    if (R == MODEL_HPP && !IRREG) {
-        if ((K == 3 && NS && SL) || (K == 4 && NS && !SL)) return 32;
-        if ((K == 6 && NS && !SL) || (K == 7 && !NS && SL)) return 28;
-    }
-    if (R == MODEL_HPP && IRREG) {
-        if (K == 4 && NS && SL) return 24;
-        if (K == 6 && NS && SL) return 20;
-        if (K == 7 && !NS && !SL) return 28;
-    }
-    if (R == MODEL_FHP_I && IRREG) {
-        if (K == 2 && NS && SL) return 28;
-        if (K == 4 && !NS && !SL) return 24;
-    }
-    if (R == MODEL_FHP_II && !IRREG && K == 6 && NS && SL) return 16;
-    return 0; // no hint
+    return wave_pin(rule_of(MODEL), K, HAS_NS, HAS_SL, IRREG);
 }
 // Row range [oa, ob) of a tile's output, relative to the first owned row.  Whole lattices: uniform chunks.
 // Strips: tile rows 0 and 1 are the bottom and the top EDGE chunk (the only ones that read ghost rows); they are
@@ -380,7 +361,7 @@ __device__ __forceinline__ LaneSrc<IRREG, COH> make_lane_src(const Geom& g, int 
 // Rows a tile reads are not written again before it has bumped its own counter (their next writer is a tile of launch
 // n+2 in the same neighbourhood), so they are constant for the tile's lifetime.  No deadlock: the dependents of a
 // launch are dispatched only after ALL its blocks have started, so whatever a spinning tile waits for is resident or done.
-static __device__ __noinline__ void chain_wait(const WaveArgs& A, const Geom& g, const WavePlan& wp, int c, int K)
+__device__ __forceinline__ void chain_wait(const WaveArgs& A, const Geom& g, const WavePlan& wp, int c, int K)
 {
     // every lane polls (same address: one broadcast request) -- no divergent region in front of the tile body
     int oa, ob;
@@ -414,7 +395,7 @@ static __device__ __noinline__ void chain_wait(const WaveArgs& A, const Geom& g,
     }
     __threadfence();
 }
-static __device__ __noinline__ void chain_signal(const WaveArgs& A, int c)
+__device__ __forceinline__ void chain_signal(const WaveArgs& A, int c)
 {
     // every lane publishes its own stores (counters count lanes: 32 per tile)
     __threadfence();
