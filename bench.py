@@ -531,7 +531,10 @@ def run_b200_arm(args):
                 "limiter": "integer pipe + issue slots (LOP3/SHF/SHFL; sm__pipe_alu and issue_active in profiles/), not DRAM: dram_frac is the share of the copy peak the kernel really moves",
                 "note": "algorithmic bytes = sites*(2*NUM_DIR+masks)/8 per step x k fused steps per launch; "
                         "real DRAM traffic (`traffic`, ncu) is ~1/k of it (temporal blocking), so frac exceeds 1; "
-                        "dram_frac = traffic / launch time / peak"}
+                        "dram_frac = traffic / launch time / peak",
+                "launch_timing": "CUDA events on the kernel's stream around 25 consecutive launches / 25; consecutive launches of a "
+                                 "call are chained (the next launch fills the warp slots the previous one frees, ordered by "
+                                 "per-chunk completion counters), so this is the effective time per launch, not an isolated one"}
 
     line = None
     if rank == 0:
