@@ -677,14 +677,24 @@ def app_tick_extra():
         ent = {}
         exe = os.path.join(bin_dir, app)
         if os.path.exists(exe):
-            p = subprocess.run([exe, "--steps", "1000", "--quiet"] + extra, capture_output=True, text=True)
-            m = re.search(r"Tick loop: (\S+) s wall for (\d+) steps in (\d+) ticks \(mean velocity (\S+) s, body force (\S+) s, "
-                          r"stepping (\S+) s, snapshot \+ post-process (\S+) s\); (\S+) site updates/s", p.stdout)
+            # best of three runs (all wall times are kept in `wall_s_runs`): the tick loop is 0.2-0.9 s of many short device
+            # calls next to this process's own CUDA context, and single runs have shown one-off stalls of the body-force calls
+            m, p, walls = None, None, []
+            for _ in range(3):
+                p = subprocess.run([exe, "--steps", "1000", "--quiet"] + extra, capture_output=True, text=True)
+                mm = re.search(r"Tick loop: (\S+) s wall for (\d+) steps in (\d+) ticks \(mean velocity (\S+) s, body force (\S+) s, "
+                               r"stepping (\S+) s, snapshot \+ post-process (\S+) s\); (\S+) site updates/s", p.stdout)
+                if not mm or p.returncode != 0:
+                    m = None
+                    break
+                walls.append(float(mm.group(1)))
+                if m is None or float(mm.group(1)) < float(m.group(1)):
+                    m = mm
             if m and p.returncode == 0:
                 ent["b200"] = {"steps": int(m.group(2)), "ticks": int(m.group(3)), "wall_s": float(m.group(1)),
                                "mean_velocity_s": float(m.group(4)), "body_force_s": float(m.group(5)), "stepping_s": float(m.group(6)),
                                "post_process_s": float(m.group(7)), "site_updates_per_s": float(m.group(8)),
-                               "ms_per_tick": float(m.group(1)) / int(m.group(3)) * 1e3}
+                               "ms_per_tick": float(m.group(1)) / int(m.group(3)) * 1e3, "wall_s_runs": walls}
             else:
                 ent["b200"] = {"error": (p.stdout + p.stderr)[-300:]}
         try:

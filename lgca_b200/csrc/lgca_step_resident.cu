@@ -441,16 +441,10 @@ __global__ void __launch_bounds__(ResThreads<OWN>::value, 1) step_resident_kerne
     #pragma unroll
                         for (int d = 0; d < 7; ++d) n[d] = d < ND ? in[d][i] : 0u;
                         collide_and_walls<MODEL, HAS_NS, HAS_SL>(n, pch[i], pns[i], psl[i], pew[i], ns_row);
+                        // words after the last real word are padding (kept zero), the last real word may be partial
+                        const uint32_t vm = !c.lastg ? 0xFFFFFFFFu : (i < c.il ? 0xFFFFFFFFu : (i == c.il ? vm_last : 0u));
     #pragma unroll
-                        for (int d = 0; d < ND; ++d) out[d][i] = n[d];
-                    }
-                    if (c.lastg) { // words after the last real word are padding (kept zero), the last real word may be partial
-    #pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const uint32_t vm = i < c.il ? 0xFFFFFFFFu : (i == c.il ? vm_last : 0u);
-    #pragma unroll
-                            for (int d = 0; d < ND; ++d) out[d][i] &= vm;
-                        }
+                        for (int d = 0; d < ND; ++d) out[d][i] = n[d] & vm;
                     }
     #pragma unroll
                     for (int d = 0; d < ND; ++d) sts4(nxt + d * plane_sz + rc + g4, make_uint4(out[d][0], out[d][1], out[d][2], out[d][3]));

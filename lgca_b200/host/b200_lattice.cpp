@@ -1,5 +1,7 @@
 // B200_Lattice<Model> -- see b200_lattice.h.  Host C++ on top of the C-ABI; no lattice arithmetic here.
 #include "b200_lattice.h"
+#include <chrono>
+#include <cstdio>
 
 #include <algorithm>
 #include <cstring>
@@ -312,11 +314,24 @@ void B200_Lattice<model_>::apply_body_force(const int forcing)
     while ((first || remaining > 0) && it < it_max) {
         size_t want = (size_t)std::max<double>(256.0, (double)std::max<long>(remaining, 1) * m_draws_per_hit * 1.25);
         want = std::min(want, it_max - it);
+#ifdef LGCA_BF_TRACE
+        const auto tr0 = std::chrono::steady_clock::now();
+        const size_t had = draws_pending();
+#endif
         draw_until(want);
+#ifdef LGCA_BF_TRACE
+        const auto tr1 = std::chrono::steady_clock::now();
+#endif
         size_t consumed = 0;
         uint32_t reverted = 0;
         const int rc = lgca_b200_group_body_force(m_h, (int)remaining, m_draws.data() + m_draw_head, want, &consumed, &reverted);
         if (rc) fail("apply_body_force", rc);
+#ifdef LGCA_BF_TRACE
+        const auto tr2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "bf: remaining %ld want %zu had %zu consumed %zu reverted %u dph %.2f draw %.3f ms device %.3f ms\n", remaining, want, had,
+                consumed, reverted, m_draws_per_hit, std::chrono::duration<double, std::milli>(tr1 - tr0).count(),
+                std::chrono::duration<double, std::milli>(tr2 - tr1).count());
+#endif
         m_draw_head += consumed;
         it += consumed;
         remaining -= reverted;
