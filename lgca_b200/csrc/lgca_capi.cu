@@ -428,31 +428,9 @@ static int step_impl(lgca_b200_lattice* h, int n_steps, bool check_halo, int cha
         }
         uint32_t* in  = h->planes[h->cur];
         uint32_t* out = h->planes[h->cur ^ 1];
-#ifdef LGCA_B200_TUNING
-        // experiment: do chained launches still overlap with the ring's event traffic between them?
-        // 1 = event record after every launch (+ a second stream waiting on it), 2 = also a wait for that stream's
-        // event of two launches ago in front of every launch
-        static cudaEvent_t ex_a[2], ex_b[2];
-        static cudaStream_t ex_s = nullptr;
-        static uint64_t ex_n = 0;
-        const int ex_mode = getenv("LGCA_B200_CHAIN_EVENTS") ? atoi(getenv("LGCA_B200_CHAIN_EVENTS")) : 0;
-        if (ex_mode && !ex_s) {
-            cudaStreamCreateWithFlags(&ex_s, cudaStreamNonBlocking);
-            for (int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&ex_a[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ex_b[i], cudaEventDisableTiming); }
-        }
-        if (ex_mode >= 2 && ex_n >= 2) cudaStreamWaitEvent(h->s_compute, ex_b[ex_n & 1], 0);
-#endif
         if (!simple && wave_supported(h, k)) { rc = launch_step_wave(h, in, out, k, h->s_compute, prev_k == k); prev_k = k; }
         else { k = 1; rc = launch_step_simple(h, in, out, h->s_compute); prev_k = 0; }
         if (rc) return rc;
-#ifdef LGCA_B200_TUNING
-        if (ex_mode) {
-            cudaEventRecord(ex_a[ex_n & 1], h->s_compute);
-            cudaStreamWaitEvent(ex_s, ex_a[ex_n & 1], 0);
-            cudaEventRecord(ex_b[ex_n & 1], ex_s);
-            ex_n++;
-        }
-#endif
         h->cur ^= 1;
         if (h->snap_spare) { // `in` is the zero-copy snapshot: the retired snapshot buffer takes its slot in the pair
             h->planes[h->cur ^ 1] = h->snap_spare;
