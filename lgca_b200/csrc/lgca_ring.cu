@@ -234,8 +234,13 @@ int lgca_b200_ring_connect(lgca_b200_lattice* h, const void* lower_descriptor, c
     LGCA_CUDA_CHECK(cudaFuncGetAttributes(&fa, ring_push_kernel));
     LGCA_CUDA_CHECK(cudaFuncGetAttributes(&fa, ring_signal_kernel));
     LGCA_CUDA_CHECK(cudaFuncGetAttributes(&fa, ring_wait_kernel));
+    // my own push-done word restarts with the epochs (the neighbours' words in [0..3] are theirs to write)
+    LGCA_CUDA_CHECK(cudaMemsetAsync((uint32_t*)h->ring_flags + 4, 0, sizeof(uint32_t), h->s_compute));
+    LGCA_CUDA_CHECK(cudaStreamSynchronize(h->s_compute));
     h->ring_connected = 1;
     h->ring_epoch = 0;
+    h->ring_chain_k = 0;
+    h->ring_chain_run = 0;
     return 0;
 }
 
