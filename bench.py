@@ -66,7 +66,7 @@ def kernel_source_stamp():
     only attached to a bench line when they were captured from exactly this kernel."""
     import hashlib
     h = hashlib.sha256()
-    for f in ("lgca_step_wave.cu", "lgca_collide.cuh", "lgca_common.cuh"):
+    for f in ("lgca_step_wave.cu", "lgca_collide.cuh", "lgca_common.cuh", "lgca_wave_pins.h"):
         h.update(open(os.path.join(ROOT, "lgca_b200", "csrc", f), "rb").read())
     return h.hexdigest()[:16]
 
