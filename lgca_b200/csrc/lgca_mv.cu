@@ -22,6 +22,7 @@
 //
 // Everything is computed from the SNAPSHOT (the buffer post_process reads), on the post-processing stream.
 #include <math.h>
+#include <stdint.h>
 #include <string.h>
 #include <time.h>
 
@@ -204,69 +205,53 @@ static void mv_walk_component(const MvTables& T, const int32_t* rec, const uint8
     const uint32_t spr = (dim_x + MV_SEG_CELLS - 1) / MV_SEG_CELLS;
     const size_t   nseg = (size_t)spr * rows;
     const int64_t  LO = (int64_t)1 << 23, HI = (int64_t)1 << 24;
-    {
-        float s = *sum; // plain IEEE float32 additions (x86-64 SSE scalar adds; the host code is built without -ffast-math)
-        for (uint32_t row = 0; row < rows; ++row)
-            for (uint32_t k = 0; k < spr; ++k) {
-                const size_t   seg = (size_t)row * spr + k;
-                const uint32_t x0 = k * MV_SEG_CELLS, n = std::min<uint32_t>(MV_SEG_CELLS, dim_x - x0);
-                bool  fast = false;
-                const float sv = s;
-                if (sv != 0.0f && isfinite(sv)) {
-                    const int e = ilogbf(fabsf(sv)), idx = e - MV_E_MIN;
-                    if (idx >= 0 && idx < MV_NE) {
-                        const int64_t S = (int64_t)ldexpf(sv, 23 - e); // exact: |S| in [2^23, 2^24)
-                        const int32_t* q = rec + mv_rec_index((c * 2 + (int)(S & 1)) * MV_NE + idx, seg, nseg);
-                        const int64_t lo = q[1], hi = q[2];
-                        if (hi < lo) fast = true; // no addend in this segment
-                        else if (S > 0 ? (S + lo > LO && S + hi < HI) : (S + hi < -LO && S + lo > -HI)) {
-                            s = ldexpf((float)(S + q[0]), e - 23);
-                            fast = true;
-                        }
-                    }
+    // The accumulator lives in one of two forms: a float32 `a` (below 2^MV_E_MIN, at zero, beyond the tabulated binades),
+    // or -- for as long as it stays inside one binade -- the pair (e, S) with a = S * 2^(e-23), |S| in [2^23, 2^24).  In
+    // the second form a whole segment is one integer add and nothing is converted in between (the float32 value is
+    // formed again only where the accumulator leaves its binade: plain IEEE float32 additions, x86-64 SSE scalar adds;
+    // the host code is built without -ffast-math).
+    float    a = *sum;
+    int      e = 0, idx = -1; // idx >= 0: integer form
+    int64_t  S = 0;
+    auto to_integer = [&]() {
+        idx = -1;
+        if (a != 0.0f && isfinite(a)) {
+            e = ilogbf(fabsf(a));
+            const int i = e - MV_E_MIN;
+            if (i >= 0 && i < MV_NE) { idx = i; S = (int64_t)ldexpf(a, 23 - e); } // exact
+        }
+    };
+    auto to_float = [&]() { a = ldexpf((float)S, e - 23); idx = -1; };
+    uint64_t n_fast = 0, n_walked = 0;
+    to_integer();
+    for (uint32_t row = 0; row < rows; ++row)
+        for (uint32_t k = 0; k < spr; ++k) {
+            const size_t seg = (size_t)row * spr + k;
+            if (idx < 0) to_integer();
+            if (idx >= 0) {
+                const int32_t* q = rec + mv_rec_index((c * 2 + (int)(S & 1)) * MV_NE + idx, seg, nseg);
+                const int64_t lo = q[1], hi = q[2];
+                if (hi < lo) { ++n_fast; continue; } // no addend in this segment
+                if (S > 0 ? (S + lo > LO && S + hi < HI) : (S + hi < -LO && S + lo > -HI)) {
+                    S += q[0];
+                    ++n_fast;
+                    continue;
                 }
-                if (stats) stats[fast ? 0 : 1]++;
-                if (fast) continue;
-                // a binade boundary (or zero) is crossed inside this segment: cell by cell.  Inside a binade the adds are
-                // still integer adds (one-cycle dependency chain where the binade has no tie class); the add that
-                // leaves the binade, and everything below 2^MV_E_MIN, is a real float32 addition.
-                const uint8_t* p = cls + (size_t)row * dim_x + x0;
-                const float*   tv = T.v[c];
-                float    a = s;
-                uint32_t i = 0;
-                while (i < n) {
-                    if (a != 0.0f && isfinite(a)) {
-                        const int e = ilogbf(fabsf(a)), idx = e - MV_E_MIN;
-                        if (idx >= 0 && idx < MV_NE) {
-                            int64_t        S = (int64_t)ldexpf(a, 23 - e);
-                            const int64_t  lo = S > 0 ? LO : -HI, hi = S > 0 ? HI : -LO; // results must stay strictly inside
-                            const int32_t* tr = T.rt[c][idx];
-                            if (!T.has_tie[c][idx]) {
-                                for (; i < n; ++i) {
-                                    const int64_t S2 = S + (tr[p[i]] >> 1);
-                                    if (!(S2 > lo && S2 < hi)) break;
-                                    S = S2;
-                                }
-                            } else {
-                                for (; i < n; ++i) {
-                                    const int32_t r = tr[p[i]];
-                                    int64_t S2 = S + (r >> 1);
-                                    S2 += S2 & r & 1; // tie: to the even neighbour
-                                    if (!(S2 > lo && S2 < hi)) break;
-                                    S = S2;
-                                }
-                            }
-                            a = ldexpf((float)S, e - 23);
-                            if (i == n) break;
-                        }
-                    }
-                    a += tv[p[i]];
-                    ++i;
-                }
-                s = a;
             }
-        *sum = s;
-    }
+            ++n_walked;
+            // a binade boundary (or zero) is crossed inside this segment: the reference's own float32 additions, cell by
+            // cell.  (Measured on the host: integer adds inside the binade with a conversion at every exit were SLOWER here
+            // than the plain 4-cycle add chain -- the walked segments are mostly those of the undriven component close to
+            // zero, where the binades are narrow and almost every add leaves them: 3.4 -> 1.5 ms on the Karman default.)
+            if (idx >= 0) to_float();
+            const uint32_t x0 = k * MV_SEG_CELLS, n = std::min<uint32_t>(MV_SEG_CELLS, dim_x - x0);
+            const uint8_t* p = cls + (size_t)row * dim_x + x0;
+            const float*   tv = T.v[c];
+            for (uint32_t i = 0; i < n; ++i) a += tv[p[i]];
+        }
+    if (idx >= 0) to_float();
+    *sum = a;
+    if (stats) { stats[0] += n_fast; stats[1] += n_walked; }
 }
 
 // the two components are independent chains: y walks on a helper thread while x walks here
